@@ -1,0 +1,234 @@
+/* gadfit_b200 -- C-ABI of the B200-native Levenberg-Marquardt inner loop.
+ *
+ * Drop-in boundary for the hot path of GADfit's global multi-dataset fit:
+ * every entry point below replaces one piece of the reference solver
+ * interface gadfit::LMsolver (reference c++/gadfit/lm_solver.h:146-211) and
+ * is what a cgo / JNI / ISO_C_BINDING / ctypes binding of that interface
+ * would bind.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Call order and error behaviour are those of the reference:
+ *   create -> add_dataset (all of them) -> set_par (...) -> [set_settings]
+ *   -> fit -> get_par / chi2 / get_array ...
+ * Every function returns a gadfit_b200_status; a non-zero status corresponds
+ * to the reference exception of the same name (exceptions.h:21-80) or to a
+ * device-side failure.  Nothing here ever falls back to a CPU path: without a
+ * usable CUDA device fit()/chi2()/get_value() return GADFIT_B200_CUDA_ERROR.
+ */
+#ifndef GADFIT_B200_H
+#define GADFIT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gadfit_b200_solver gadfit_b200_solver;
+
+typedef enum gadfit_b200_status
+{
+    GADFIT_B200_OK = 0,
+    /* reference exceptions, c++/gadfit/exceptions.h:24-78 */
+    GADFIT_B200_UNKNOWN_OPERATION = 1,
+    GADFIT_B200_LATE_ADD_DATASET_CALL = 2,    /* lm_solver.cpp:35-37 */
+    GADFIT_B200_SET_PAR_INVALID_INDEX = 3,    /* lm_solver.cpp:65-68 */
+    GADFIT_B200_UNINITIALIZED_PARAMETER = 4,  /* lm_solver.cpp:145-149 */
+    GADFIT_B200_NEGATIVE_DEGREES_OF_FREEDOM = 5, /* lm_solver.cpp:137-139 */
+    GADFIT_B200_NO_FITTING_PARAMETERS = 6,    /* lm_solver.cpp:187-189 */
+    GADFIT_B200_NO_GLOBAL_PARAMETERS = 7,     /* lm_solver.cpp:129-131 */
+    GADFIT_B200_INSUFFICIENT_INTEGRATION_WORKSPACE = 8,
+    /* conditions that have no reference counterpart */
+    GADFIT_B200_UNKNOWN_MODEL = 9,
+    GADFIT_B200_CUDA_ERROR = 10,
+    GADFIT_B200_NCCL_ERROR = 11,
+    GADFIT_B200_INVALID_ARGUMENT = 12,
+    GADFIT_B200_NOT_AVAILABLE = 13
+} gadfit_b200_status;
+
+/* Loss functions, lm_solver.h:77-82 */
+enum
+{
+    GADFIT_B200_LOSS_LINEAR = 0,
+    GADFIT_B200_LOSS_CAUCHY = 1,
+    GADFIT_B200_LOSS_HUBER = 2
+};
+
+/* POD mirror of LMsolver::settings, lm_solver.h:198-210 (defaults :88-96) */
+typedef struct gadfit_b200_settings
+{
+    int iteration_limit;           /* 1000 */
+    int lambda_incs;               /* 3 */
+    double lambda_down;            /* 10 */
+    double lambda_up;              /* 10 */
+    int damp_max;                  /* 1 */
+    const double* DTD_min;         /* NULL; used only if n_DTD_min > 1, */
+    int n_DTD_min;                 /*   as in lm_solver.cpp:424-428 */
+    double acceleration_threshold; /* -1 (off) */
+    unsigned verbosity;            /* io::flag bits, lm_solver.h:60-72 */
+    int loss;                      /* GADFIT_B200_LOSS_LINEAR */
+    int n_threads;                 /* accepted for source compatibility; the
+                                      data-parallel width is the GPU's */
+} gadfit_b200_settings;
+
+/* Arrays readable after fit(), lm_solver.h:188-194 (+ the step vectors) */
+typedef enum gadfit_b200_array
+{
+    GADFIT_B200_JACOBIAN = 0,  /* dense N x n, row major; small problems only */
+    GADFIT_B200_JTJ = 1,       /* dense n x n */
+    GADFIT_B200_DTD = 2,       /* dense n x n (diagonal) */
+    GADFIT_B200_LEFT_SIDE = 3, /* dense n x n, JTJ + lambda DTD */
+    GADFIT_B200_RIGHT_SIDE = 4, /* n */
+    GADFIT_B200_RESIDUALS = 5, /* N */
+    GADFIT_B200_INV_JTJ = 6,   /* dense n x n */
+    GADFIT_B200_DELTA1 = 7,    /* n */
+    GADFIT_B200_DELTA2 = 8,    /* n (zeros unless acceleration is on) */
+    GADFIT_B200_OMEGA = 9      /* N (acceleration only) */
+} gadfit_b200_array;
+
+/* One record per trial step: the reference prints exactly this at debug
+ * level, "Current lambda: {}, new chi2 = {}, old chi2: {}"
+ * (lm_solver.cpp:457-460).  decision: 0 = accepted (:462-468), 1 = rejected,
+ * lambda raised and step recomputed (:470-481), 2 = rejected and given up
+ * (:482-494). */
+typedef struct gadfit_b200_trial
+{
+    double lambda;
+    double new_chi2;
+    double old_chi2;
+    int iteration;
+    int decision;
+} gadfit_b200_trial;
+
+/* The five phase timers of the reference (lm_solver.h:140-144, table printed
+ * by lm_solver.cpp:656-680): seconds of device time (CUDA events) and number
+ * of calls, in the order Jacobian, chi2, linear algebra, omega, main loop. */
+typedef struct gadfit_b200_timings
+{
+    double seconds[5];
+    int calls[5];
+} gadfit_b200_timings;
+
+/* LMsolver::LMsolver(fitSignature), lm_solver.h:148.  The fitting function is
+ * selected by name from the functions compiled into the library
+ * (include/gadfit_b200/fit_models.h); a std::function cannot run on the
+ * device. */
+int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out);
+int gadfit_b200_destroy(gadfit_b200_solver* solver);
+
+/* Number of registered fitting functions / name and parameter count of one */
+int gadfit_b200_n_models(void);
+int gadfit_b200_model_info(int i_model, const char** name, int* n_pars);
+
+/* LMsolver::addDataset(n, x, y, errors = nullptr), lm_solver.h:164-167,
+ * lm_solver.cpp:30-56.  Arrays are BORROWED until fit() has uploaded them
+ * (first fit() or gadfit_b200_upload()).  With a communicator attached, x/y
+ * may be NULL on ranks that do not own the dataset (see
+ * gadfit_b200_owned_datasets). */
+int gadfit_b200_add_dataset(gadfit_b200_solver* solver,
+                            int n_datapoints,
+                            const double* x_data,
+                            const double* y_data,
+                            const double* errors_or_null);
+
+/* LMsolver::setPar(i_par, val, active, i_dataset = -1, name = ""),
+ * lm_solver.h:171-180, lm_solver.cpp:58-113.  i_dataset = -1: global. */
+int gadfit_b200_set_par(gadfit_b200_solver* solver,
+                        int i_par,
+                        double val,
+                        int active,
+                        int i_dataset,
+                        const char* name_or_null);
+
+/* LMsolver::settings, lm_solver.h:198-210 */
+int gadfit_b200_default_settings(gadfit_b200_settings* out);
+int gadfit_b200_set_settings(gadfit_b200_solver* solver,
+                             const gadfit_b200_settings* settings);
+
+/* LMsolver::fit(lambda = 10), lm_solver.h:181, lm_solver.cpp:401-511 */
+int gadfit_b200_fit(gadfit_b200_solver* solver, double lambda);
+
+/* getParValue / getValue / chi2 / degreesOfFreedom,
+ * lm_solver.h:182-187,195, lm_solver.cpp:513-534,688-696 */
+int gadfit_b200_get_par(gadfit_b200_solver* solver,
+                        int i_par,
+                        int i_dataset,
+                        double* out);
+int gadfit_b200_get_value(gadfit_b200_solver* solver,
+                          double arg,
+                          int i_dataset,
+                          double* out);
+int gadfit_b200_chi2(gadfit_b200_solver* solver, double* out);
+int gadfit_b200_dof(gadfit_b200_solver* solver, int* out);
+
+/* getJacobian/getJTJ/getDTD/getLeftSide/getRightSide/getResiduals/getInvJTJ,
+ * lm_solver.h:188-194, lm_solver.cpp:536-585.  Writes min(cap, need) doubles;
+ * *need is the full length.  Dense n x n / N x n outputs are materialised on
+ * demand from the block-arrow storage and refused with
+ * GADFIT_B200_NOT_AVAILABLE beyond 2^27 entries. */
+int gadfit_b200_get_array(gadfit_b200_solver* solver,
+                          int which,
+                          double* buf,
+                          size_t cap,
+                          size_t* need);
+
+/* Accept/reject history of the last fit() (see gadfit_b200_trial) */
+int gadfit_b200_get_trace(gadfit_b200_solver* solver,
+                          gadfit_b200_trial* buf,
+                          size_t cap,
+                          size_t* n);
+/* Number of successful iterations of the last fit(), lm_solver.cpp:439-501 */
+int gadfit_b200_n_iterations(gadfit_b200_solver* solver, int* out);
+int gadfit_b200_get_timings(gadfit_b200_solver* solver,
+                            gadfit_b200_timings* out);
+/* Kernels launched by this solver since creation */
+int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out);
+/* Average device time [s] of the Jacobian-sweep kernel alone in the last
+ * fit() (CUDA events on the solver's stream) and the number of launches */
+int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
+                                     double* seconds_per_launch,
+                                     int* launches);
+
+const char* gadfit_b200_last_error(gadfit_b200_solver* solver);
+const char* gadfit_b200_status_name(int status);
+
+/* ---- device / multi-GPU plumbing (no reference counterpart) ------------- */
+
+/* CUDA device of this solver (default: the current device at create) */
+int gadfit_b200_set_device(gadfit_b200_solver* solver, int device);
+/* Copy the borrowed data sets to HBM now instead of at the first fit() */
+int gadfit_b200_upload(gadfit_b200_solver* solver);
+
+/* One process per GPU.  Rank 0 obtains an id, the caller broadcasts the 128
+ * bytes (torch.distributed / MPI / sockets) and every rank attaches.  All
+ * ranks then describe the SAME global problem (same add_dataset / set_par
+ * calls, as the images of the Fortran coarray version do,
+ * fortran/gadfit/gadfit.F90:539-551); each rank uploads and sweeps only the
+ * data sets (or the slice of points) it owns, and only the shared-parameter
+ * normal block, its right-hand side and chi2 are all-reduced per trial step
+ * (the reference's co_sum of the dense JTJ, gadfit.F90:700-701,735,1032). */
+int gadfit_b200_comm_unique_id(void* id_128_bytes);
+int gadfit_b200_set_comm(gadfit_b200_solver* solver,
+                         int rank,
+                         int world_size,
+                         const void* id_128_bytes);
+/* Partition used for (n_datasets, points per data set) on (rank, world):
+ * first/last+1 owned data set, or -- when there are fewer data sets than
+ * ranks -- every data set with the point slice [*point_begin, *point_end)
+ * expressed as fractions k/world of each data set (then *split = 1). */
+int gadfit_b200_partition(int n_datasets,
+                          const int* n_points,
+                          int rank,
+                          int world_size,
+                          int* first_dataset,
+                          int* end_dataset,
+                          int* split);
+
+/* FP64 FMA peak of the current device measured by a register-resident DFMA
+ * loop on every SM [FLOP/s]; the roofline denominator of bench.py */
+int gadfit_b200_measure_fp64_peak(double* flops_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GADFIT_B200_H */

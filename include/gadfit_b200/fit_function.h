@@ -1,0 +1,104 @@
+// Evaluation contexts: how a fitting function sees its parameters.
+//
+// Counterpart of gadfit::FitFunction (reference c++/gadfit/fit_function.h:
+// 29-62, fit_function.cpp:17-61): there a std::function body receives a
+// std::vector<AdVar> whose `idx` fields were flipped by activateParReverse /
+// activateParForward / deactivatePar before each sweep.  A std::function
+// cannot cross to the device, so a fitting function here is a functor with
+//
+//     static constexpr int n_pars;
+//     template <class Ctx> GADFIT_HD auto operator()(const Ctx& c, double x) const;
+//
+// and the sweep being run is selected by the TYPE of the context:
+//
+//   ValueCtx  par<K>(c) is passive            -> chi2 sweep (lm_solver.cpp:513-529)
+//   GradCtx   par<K>(c) is SDual<1 << K>      -> Jacobian sweep (lm_solver.cpp:286-322)
+//   Dir2Ctx   par<K>(c) is Dir2 seeded with   -> omega sweep (lm_solver.cpp:362-380,
+//             d = delta1[column], dd = 0         fit_function.cpp:45-51)
+//
+// c.kronrod(...) / c.kronrod2d(...) give the fixed 15-point Kronrod panel of
+// the reference (numerical_integration.cpp:133-148,189-215).
+#pragma once
+
+#include "dual.h"
+#include "quadrature.h"
+
+namespace gadfit_b200 {
+
+struct QuadratureMixin
+{
+    template <class F>
+    GADFIT_HD auto kronrod(const double lower, const double upper, F&& f) const
+    {
+        return gadfit_b200::kronrod(lower, upper, f);
+    }
+    template <class F>
+    GADFIT_HD auto kronrod2d(const double outer_lower,
+                             const double outer_upper,
+                             const double inner_lower,
+                             const double inner_upper,
+                             F&& f) const
+    {
+        return gadfit_b200::kronrod2d(
+          outer_lower, outer_upper, inner_lower, inner_upper, f);
+    }
+};
+
+struct ValueCtx : QuadratureMixin
+{
+    const double* p;
+    template <int K>
+    GADFIT_HD Passive get() const
+    {
+        return Passive { p[K] };
+    }
+};
+
+struct GradCtx : QuadratureMixin
+{
+    const double* p;
+    template <int K>
+    GADFIT_HD SDual<(1U << K)> get() const
+    {
+        SDual<(1U << K)> y;
+        y.val = p[K];
+        y.d[0] = 1.0;
+        return y;
+    }
+};
+
+struct Dir2Ctx : QuadratureMixin
+{
+    const double* p;
+    // Direction: delta1 of the column this parameter maps to, 0 if passive
+    const double* seed;
+    template <int K>
+    GADFIT_HD Dir2 get() const
+    {
+        return Dir2 { p[K], seed[K], 0.0 };
+    }
+};
+
+// par<K>(ctx): parameter K in the AD type of the current sweep
+template <int K, class Ctx>
+GADFIT_HD auto par(const Ctx& c)
+{
+    return c.template get<K>();
+}
+
+// Value of any AD type
+GADFIT_HD double value_of(const double x)
+{
+    return x;
+}
+template <uint32_t M>
+GADFIT_HD double value_of(const SDual<M>& x)
+{
+    return x.val;
+}
+GADFIT_HD double value_of(const Dir2& x)
+{
+    return x.val;
+}
+
+} // namespace gadfit_b200

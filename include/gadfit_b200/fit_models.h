@@ -1,0 +1,146 @@
+// Fitting functions compiled into the library ("model registry").
+//
+// A fitting function is user code: in the reference it is the lambda handed
+// to gadfit::LMsolver (c++/tests/example.cpp:11-19).  Here it is a functor
+// templated on the evaluation context (fit_function.h), so that ONE source
+// of each function is compiled three ways:
+//   * into the sm_100a kernels (SDual / Dir2 / passive),
+//   * against the UNMODIFIED reference's gadfit::AdVar (oracle/ref_harness.cpp),
+//   * against the oracle's own dense forward-mode dual (oracle/oracle_solver.cpp),
+// which is what makes "identical inputs" in the parity tests literal.
+//
+// Functions and parameter layouts (BASELINE.json configs):
+//   exponential          I0*exp(-x/tau)+bgr              [I0, tau, bgr]
+//   gauss_hermite3       sum of 3 distorted Gaussians    [A,mu,w,a,b,c] x3, b0, b1
+//   gauss_linear_bg      A e^{-u^2}(1+s u)+b0+b1 x       [A, mu, w, s, b0, b1]
+//   conv_exp_gauss       single-integral model           [A, tau, sg, t0, bgr]
+//   lorentz_double_int   double-integral model           [A, x0, gamma, b, c, k1, k2]
+#pragma once
+
+#include "fit_function.h"
+
+namespace gadfit_b200::models {
+
+// c++/tests/lm_solver.cpp:11-19 (also c++/tests/example.cpp:11-19)
+struct Exponential
+{
+    static constexpr int n_pars { 3 };
+    static constexpr const char* name { "exponential" };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto I0 { par<0>(c) };
+        const auto tau { par<1>(c) };
+        const auto bgr { par<2>(c) };
+        return I0 * exp(-x / tau) + bgr;
+    }
+};
+
+// BASELINE config 2: "sum-of-3-Gaussians model, 20 shared params".  Each
+// peak is a Gaussian with a cubic Gauss-Hermite-style distortion,
+//   A e^{-u^2} (1 + a u + b u^2 + c u^3),  u = (x - mu) / w,
+// plus a linear background b0 + b1 x: 3 x 6 + 2 = 20 parameters.
+struct GaussHermite3
+{
+    static constexpr int n_pars { 20 };
+    static constexpr const char* name { "gauss_hermite3" };
+
+    template <int K, class Ctx>
+    GADFIT_HD static auto peak(const Ctx& c, const double x)
+    {
+        const auto u { (x - par<6 * K + 1>(c)) / par<6 * K + 2>(c) };
+        const auto e { exp(-(u * u)) };
+        const auto poly {
+            1.0 + u * (par<6 * K + 3>(c) + u * (par<6 * K + 4>(c) + u * par<6 * K + 5>(c)))
+        };
+        return par<6 * K>(c) * e * poly;
+    }
+
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        return peak<0>(c, x) + peak<1>(c, x) + peak<2>(c, x) + par<18>(c)
+               + par<19>(c) * x;
+    }
+};
+
+// BASELINE config 3: "Gaussian peak + linear background: 4 local + 2 shared".
+// Shared (w, s); local (A, mu, b0, b1).
+struct GaussLinearBg
+{
+    static constexpr int n_pars { 6 };
+    static constexpr const char* name { "gauss_linear_bg" };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto u { (x - par<1>(c)) / par<2>(c) };
+        return par<0>(c) * exp(-(u * u)) * (1.0 + par<3>(c) * u) + par<4>(c)
+               + par<5>(c) * x;
+    }
+};
+
+// BASELINE config 4: "model with per-point single integral (Gaussian-
+// convolved exponential via fixed Gauss-Legendre[-Kronrod])":
+//   A * int_0^T e^{-t/tau} e^{-((x-t-t0)/sg)^2} / (sg sqrt(pi)) dt + bgr,
+// T = 10, one 15-node Kronrod panel.  Shared (tau, sg, t0); local (A, bgr).
+struct ConvExpGauss
+{
+    static constexpr int n_pars { 5 };
+    static constexpr const char* name { "conv_exp_gauss" };
+    static constexpr double upper_bound { 10.0 };
+    static constexpr double sqrt_pi { 1.7724538509055160272981674833411451 };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto tau { par<1>(c) };
+        const auto sg { par<2>(c) };
+        const auto t0 { par<3>(c) };
+        const auto integral { c.kronrod(0.0, upper_bound, [&](const auto& t) {
+            const auto z { (x - t - t0) / sg };
+            return exp(-t / tau) * exp(-(z * z)) / (sg * sqrt_pi);
+        }) };
+        return par<0>(c) * integral + par<4>(c);
+    }
+};
+
+// BASELINE config 5: "Lorentzian + background with double-integral term,
+// 3 local + 4 shared":
+//   A g^2/((x-x0)^2+g^2) + b + c * int_0^1 int_0^1 e^{-k1 u^2 - k2 v^2}
+//                                       / (1 + (x-u-v)^2) du dv,
+// 15 x 15 Kronrod.  Shared (gamma, c, k1, k2); local (A, x0, b).
+struct LorentzDoubleInt
+{
+    static constexpr int n_pars { 7 };
+    static constexpr const char* name { "lorentz_double_int" };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto g { par<2>(c) };
+        const auto k1 { par<5>(c) };
+        const auto k2 { par<6>(c) };
+        const auto dx { x - par<1>(c) };
+        const auto g2 { g * g };
+        const auto lorentz { par<0>(c) * g2 / (dx * dx + g2) };
+        const auto integral { c.kronrod2d(
+          0.0, 1.0, 0.0, 1.0, [&](const auto& u, const auto& v) {
+              const auto s { x - u - v };
+              return exp(-(k1 * (u * u)) - k2 * (v * v)) / (1.0 + s * s);
+          }) };
+        return lorentz + par<3>(c) + par<4>(c) * integral;
+    }
+};
+
+// Calls f.template operator()<Model>() for every registered model; the
+// library, the reference harness and the oracle all dispatch through this
+// one list.
+template <class F>
+inline void for_each_model(F&& f)
+{
+    f.template operator()<Exponential>();
+    f.template operator()<GaussHermite3>();
+    f.template operator()<GaussLinearBg>();
+    f.template operator()<ConvExpGauss>();
+    f.template operator()<LorentzDoubleInt>();
+}
+
+} // namespace gadfit_b200::models
