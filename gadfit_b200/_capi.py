@@ -77,7 +77,7 @@ CORE_SYMBOLS = [
 PRODUCT_ONLY_SYMBOLS = [
     "n_models", "model_info", "n_launches", "jacobian_kernel_time",
     "status_name", "set_device", "upload", "comm_unique_id", "set_comm",
-    "partition", "measure_fp64_peak",
+    "partition", "measure_fp64_peak", "microbench",
 ]
 
 
@@ -126,6 +126,7 @@ class Api:
                 "set_comm": ([vp, C.c_int, C.c_int, vp], C.c_int),
                 "partition": ([C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),
                 "measure_fp64_peak": ([c_double_p], C.c_int),
+                "microbench": ([C.c_int, c_double_p], C.c_int),
             })
         for name, (argtypes, restype) in sig.items():
             fn = getattr(self.lib, prefix + name)

@@ -1,0 +1,565 @@
+// Block-arrow normal equations: batched per-data-set Cholesky, Schur
+// complement onto the shared parameters, damped solve, step bookkeeping
+// (sm_100a).
+//
+// The reference assembles the dense n x n matrix J^T J, adds lambda * DTD and
+// Cholesky-factorises it (lm_solver.cpp:325-332,348-354,383-384 via
+// lapack.cpp / lapack_fallback.cpp).  With n = p_g + sum_s p_l(s) this is
+// infeasible for many data sets (n = 300 004 in BASELINE config 5).  The
+// matrix is block-arrow:
+//
+//       [ G    C_1  C_2 ... ]   G   shared x shared   (sum over data sets)
+//   A = [ C_1' L_1          ]   C_s shared x local_s
+//       [ C_2'      L_2     ]   L_s local_s x local_s
+//
+// so (A + lambda D) delta = rhs is solved exactly by
+//   L~_s = L_s + lambda D_s = R_s R_s'            (one thread per data set)
+//   Y_s = R_s^-1 C_s',  z_s = R_s^-1 b_s
+//   (G + lambda D_g - sum_s Y_s' Y_s) delta_g = b_g - sum_s Y_s' z_s
+//   delta_s = R_s^-T (z_s - Y_s delta_g)
+// Every block is read from the per-data-set augmented matrix M_s produced by
+// the Jacobian sweep (sweep_kernels.cuh).
+//
+// Parameter roles of data set s are two bit masks over the NP model
+// parameters: `active[s]` (lm_solver.h:37, Indices::active) and the solver-wide
+// `global_mask` (lm_solver.h:42, Indices::global); local = active & ~global.
+#pragma once
+
+#include "sweep_kernels.cuh"
+
+namespace gadfit_b200 {
+
+// Device-resident state of the LM iteration (lambda schedule and accept /
+// reject logic of lm_solver.cpp:438-501 live here, not on the host)
+struct LmState
+{
+    double lambda;
+    double old_chi2;
+    double new_chi2;
+    double acc_ratio;
+    int decision;   // 0 accept, 1 retry, 2 give up (gadfit_b200_trial)
+    int i_lambda;   // consecutive rejections in this iteration
+    int use_delta2; // acceleration passed the ratio test
+    int pad;
+};
+
+// Per-data-set factorisation kept between the Schur step and the
+// back-substitution of the same trial
+template <int NP>
+struct LocalFactor
+{
+    double R[NP * NP]; // lower Cholesky factor of L_s + lambda D_s (pl x pl)
+    double Y[NP * NP]; // R^-1 C_s'  (pl x pg)
+    double z[NP];      // R^-1 b_s   (pl)
+};
+
+template <int NP>
+__device__ __forceinline__ void role_lists(const unsigned active,
+                                           const unsigned global_mask,
+                                           int (&idx_g)[NP],
+                                           int& pg,
+                                           int (&idx_l)[NP],
+                                           int& pl)
+{
+    pg = 0;
+    pl = 0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        if (((active >> k) & 1U) != 0U) {
+            if (((global_mask >> k) & 1U) != 0U) {
+                idx_g[pg++] = k;
+            } else {
+                idx_l[pl++] = k;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double m_entry(const double* __restrict__ M,
+                                          const int NA,
+                                          const int a,
+                                          const int b)
+{
+    return a <= b ? M[tri_index(NA, a, b)] : M[tri_index(NA, b, a)];
+}
+
+// Sum the partial rows of each data set in slot order (fixed => deterministic)
+// out[s][v] = sum_{slot in [first[s], first[s]+count[s])} partials[slot][v]
+__global__ void k_reduce_slots(const double* __restrict__ partials,
+                               const int* __restrict__ slot_first,
+                               const int* __restrict__ slot_count,
+                               const int n_sets,
+                               const int V,
+                               double* __restrict__ out)
+{
+    const long long idx { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
+    if (idx >= static_cast<long long>(n_sets) * V) {
+        return;
+    }
+    const int s { static_cast<int>(idx / V) };
+    const int v { static_cast<int>(idx - static_cast<long long>(s) * V) };
+    double sum { 0.0 };
+    const int first { slot_first[s] };
+    const int count { slot_count[s] };
+    for (int c = 0; c < count; ++c) {
+        sum += partials[static_cast<long long>(first + c) * V + v];
+    }
+    out[idx] = sum;
+}
+
+// Column sums over rows in two fixed stages: stage 1, block b sums rows
+// [b*chunk, (b+1)*chunk) for every column; stage 2 (gridDim == 1, chunk ==
+// number of stage-1 blocks) sums the block results.
+__global__ void k_column_sums(const double* __restrict__ in,
+                              const int n_rows,
+                              const int V,
+                              const int chunk,
+                              double* __restrict__ out)
+{
+    const int r0 { static_cast<int>(blockIdx.x) * chunk };
+    const int r1 { min(n_rows, r0 + chunk) };
+    for (int v = static_cast<int>(threadIdx.x); v < V; v += blockDim.x) {
+        double sum { 0.0 };
+        for (int r = r0; r < r1; ++r) {
+            sum += in[static_cast<long long>(r) * V + v];
+        }
+        out[static_cast<long long>(blockIdx.x) * V + v] = sum;
+    }
+}
+
+// Final stage of the chi2 sweep: sum the CTA partials in order
+__global__ void k_sum_partials(const double* __restrict__ partials,
+                               const int n,
+                               double* __restrict__ out)
+{
+    __shared__ double s_red[kThreads / 32];
+    double sum { 0.0 };
+    for (int i = static_cast<int>(threadIdx.x); i < n; i += kThreads) {
+        sum += partials[i];
+    }
+    const double total { block_sum(sum, s_red) };
+    if (threadIdx.x == 0) {
+        *out = total;
+    }
+}
+
+// Once per iteration (lm_solver.cpp:326-329 restricted to the local columns
+// + the shared-block rows of dsyrk/dgemv, :325,:339): update the local part of
+// the damping matrix and emit this data set's contribution to the shared
+// block: [G_s (pg x pg packed upper), b_g,s (pg)].
+template <int NP>
+__global__ void k_local_prepare(const double* __restrict__ M,
+                                const unsigned* __restrict__ active,
+                                const unsigned global_mask,
+                                const int n_sets,
+                                const int damp_max,
+                                double* __restrict__ dtd_local, // [n_sets][NP]
+                                double* __restrict__ contrib,   // [n_sets][VG]
+                                const int VG)
+{
+    constexpr int NA { NP + 1 };
+    constexpr int NT { NA * (NA + 1) / 2 };
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    const double* Ms { M + static_cast<long long>(s) * NT };
+    int idx_g[NP];
+    int idx_l[NP];
+    int pg;
+    int pl;
+    role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
+    for (int a = 0; a < pl; ++a) {
+        const int k { idx_l[a] };
+        const double jtj { Ms[tri_index(NA, k, k)] };
+        double* d { dtd_local + static_cast<long long>(s) * NP + k };
+        // std::max(DTD, JTJ), lm_solver.cpp:328
+        *d = damp_max != 0 ? ((*d < jtj) ? jtj : *d) : jtj;
+    }
+    double* out { contrib + static_cast<long long>(s) * VG };
+    int o { 0 };
+    for (int a = 0; a < pg; ++a) {
+        for (int b = a; b < pg; ++b) {
+            out[o++] = Ms[tri_index(NA, idx_g[a], idx_g[b])];
+        }
+    }
+    for (int a = 0; a < pg; ++a) {
+        out[o++] = Ms[tri_index(NA, idx_g[a], NP)];
+    }
+}
+
+// Per trial step: factorise the damped local block and emit the Schur
+// contribution [Y'Y (pg x pg packed upper), Y'z (pg)].  The Cholesky loop
+// order is that of the reference's in-tree dpptrf (lapack_fallback.cpp:59-81).
+template <int NP>
+__global__ void k_local_schur(const double* __restrict__ M,
+                              const unsigned* __restrict__ active,
+                              const unsigned global_mask,
+                              const int n_sets,
+                              const double* __restrict__ dtd_local,
+                              const LmState* __restrict__ state,
+                              LocalFactor<NP>* __restrict__ factors,
+                              double* __restrict__ contrib,
+                              const int VG)
+{
+    constexpr int NA { NP + 1 };
+    constexpr int NT { NA * (NA + 1) / 2 };
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    const double lambda { state->lambda };
+    const double* Ms { M + static_cast<long long>(s) * NT };
+    int idx_g[NP];
+    int idx_l[NP];
+    int pg;
+    int pl;
+    role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
+    LocalFactor<NP>& F { factors[s] };
+    // R R' = L_s + lambda D_s
+    for (int i = 0; i < pl; ++i) {
+        for (int j = 0; j < i; ++j) {
+            double v { m_entry(Ms, NA, idx_l[i], idx_l[j]) };
+            for (int k = 0; k < j; ++k) {
+                v -= F.R[i * NP + k] * F.R[j * NP + k];
+            }
+            F.R[i * NP + j] = v / F.R[j * NP + j];
+        }
+        double v { Ms[tri_index(NA, idx_l[i], idx_l[i])]
+                   + lambda * dtd_local[static_cast<long long>(s) * NP + idx_l[i]] };
+        for (int k = 0; k < i; ++k) {
+            v -= F.R[i * NP + k] * F.R[i * NP + k];
+        }
+        F.R[i * NP + i] = ::sqrt(v);
+    }
+    // Y = R^-1 C_s' and z = R^-1 b_s (forward substitution,
+    // lapack_fallback.cpp:88-95)
+    for (int g = 0; g <= pg; ++g) {
+        const int col { g < pg ? idx_g[g] : NP };
+        for (int i = 0; i < pl; ++i) {
+            double v { m_entry(Ms, NA, idx_l[i], col) };
+            for (int j = 0; j < i; ++j) {
+                v -= F.R[i * NP + j] * (g < pg ? F.Y[j * NP + g] : F.z[j]);
+            }
+            v /= F.R[i * NP + i];
+            if (g < pg) {
+                F.Y[i * NP + g] = v;
+            } else {
+                F.z[i] = v;
+            }
+        }
+    }
+    double* out { contrib + static_cast<long long>(s) * VG };
+    int o { 0 };
+    for (int a = 0; a < pg; ++a) {
+        for (int b = a; b < pg; ++b) {
+            double v { 0.0 };
+            for (int i = 0; i < pl; ++i) {
+                v += F.Y[i * NP + a] * F.Y[i * NP + b];
+            }
+            out[o++] = v;
+        }
+    }
+    for (int a = 0; a < pg; ++a) {
+        double v { 0.0 };
+        for (int i = 0; i < pl; ++i) {
+            v += F.Y[i * NP + a] * F.z[i];
+        }
+        out[o++] = v;
+    }
+}
+
+// Same factor, new right-hand side J^T omega (lm_solver.cpp:383-384):
+// z'_s = R^-1 v_s[local]; contribution [v_s[global] (pg), Y' z' (pg)].
+template <int NP>
+__global__ void k_local_schur_rhs(const double* __restrict__ v_sets, // [n_sets][NP]
+                                  const unsigned* __restrict__ active,
+                                  const unsigned global_mask,
+                                  const int n_sets,
+                                  LocalFactor<NP>* __restrict__ factors,
+                                  double* __restrict__ contrib, // [n_sets][2 pg]
+                                  const int VG2)
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    int idx_g[NP];
+    int idx_l[NP];
+    int pg;
+    int pl;
+    role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
+    LocalFactor<NP>& F { factors[s] };
+    const double* vs { v_sets + static_cast<long long>(s) * NP };
+    for (int i = 0; i < pl; ++i) {
+        double v { vs[idx_l[i]] };
+        for (int j = 0; j < i; ++j) {
+            v -= F.R[i * NP + j] * F.z[j];
+        }
+        F.z[i] = v / F.R[i * NP + i];
+    }
+    double* out { contrib + static_cast<long long>(s) * VG2 };
+    for (int a = 0; a < pg; ++a) {
+        out[a] = vs[idx_g[a]];
+    }
+    for (int a = 0; a < pg; ++a) {
+        double v { 0.0 };
+        for (int i = 0; i < pl; ++i) {
+            v += F.Y[i * NP + a] * F.z[i];
+        }
+        out[pg + a] = v;
+    }
+}
+
+// Shared-parameter system, one thread (pg <= 32).
+//   shared_sums = [G (packed upper), b_g]            (once per iteration)
+//   schur_sums  = [sum Y'Y (packed upper), sum Y'z]  (per trial)
+// which == 1: factorise G + lambda D_g - sum Y'Y and solve for delta1_g
+//             (update_dtd != 0: first apply lm_solver.cpp:326-329 to D_g)
+// which == 2: reuse the factor, rhs = rhs2_sums[0..pg) - rhs2_sums[pg..2pg)
+constexpr int kMaxShared { 32 };
+
+__global__ void k_shared_solve(const int pg,
+                               const int which,
+                               const int update_dtd,
+                               const int damp_max,
+                               const double* __restrict__ shared_sums,
+                               const double* __restrict__ schur_sums,
+                               const double* __restrict__ rhs2_sums,
+                               const LmState* __restrict__ state,
+                               double* __restrict__ dtd_global, // [pg]
+                               double* __restrict__ chol,       // [pg*pg]
+                               double* __restrict__ delta_g)    // [pg]
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    const int ntri { pg * (pg + 1) / 2 };
+    if (which == 1) {
+        const double lambda { state->lambda };
+        if (update_dtd != 0) {
+            int o { 0 };
+            for (int a = 0; a < pg; ++a) {
+                const double jtj { shared_sums[o] };
+                const double d { dtd_global[a] };
+                dtd_global[a] = damp_max != 0 ? ((d < jtj) ? jtj : d) : jtj;
+                o += pg - a;
+            }
+        }
+        // Lower Cholesky, loop order of lapack_fallback.cpp:59-81
+        for (int i = 0; i < pg; ++i) {
+            for (int j = 0; j < i; ++j) {
+                const int o { tri_index(pg, j, i) };
+                double v { shared_sums[o] - schur_sums[o] };
+                for (int k = 0; k < j; ++k) {
+                    v -= chol[i * pg + k] * chol[j * pg + k];
+                }
+                chol[i * pg + j] = v / chol[j * pg + j];
+            }
+            const int o { tri_index(pg, i, i) };
+            double v { shared_sums[o] + lambda * dtd_global[i] - schur_sums[o] };
+            for (int k = 0; k < i; ++k) {
+                v -= chol[i * pg + k] * chol[i * pg + k];
+            }
+            chol[i * pg + i] = ::sqrt(v);
+        }
+    }
+    double y[kMaxShared];
+    for (int i = 0; i < pg; ++i) {
+        double v { which == 1 ? shared_sums[ntri + i] - schur_sums[ntri + i]
+                              : rhs2_sums[i] - rhs2_sums[pg + i] };
+        for (int j = 0; j < i; ++j) {
+            v -= chol[i * pg + j] * y[j];
+        }
+        y[i] = v / chol[i * pg + i];
+    }
+    for (int i = pg - 1; i >= 0; --i) {
+        double v { y[i] };
+        for (int j = pg - 1; j > i; --j) {
+            v -= chol[j * pg + i] * delta_g[j];
+        }
+        delta_g[i] = v / chol[i * pg + i];
+    }
+}
+
+// delta_s = R^-T (z - Y delta_g), scattered by model parameter index:
+// delta_par[s][k] = step of parameter k of data set s (0 if inactive);
+// global parameters get delta_g.
+template <int NP>
+__global__ void k_local_backsolve(const unsigned* __restrict__ active,
+                                  const unsigned global_mask,
+                                  const int n_sets,
+                                  const LocalFactor<NP>* __restrict__ factors,
+                                  const double* __restrict__ delta_g,
+                                  double* __restrict__ delta_par) // [n_sets][NP]
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    int idx_g[NP];
+    int idx_l[NP];
+    int pg;
+    int pl;
+    role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
+    const LocalFactor<NP>& F { factors[s] };
+    double d[NP];
+    for (int i = 0; i < pl; ++i) {
+        double v { F.z[i] };
+        for (int a = 0; a < pg; ++a) {
+            v -= F.Y[i * NP + a] * delta_g[a];
+        }
+        d[i] = v;
+    }
+    // Backward substitution, lapack_fallback.cpp:96-104
+    for (int i = pl - 1; i >= 0; --i) {
+        double v { d[i] };
+        for (int j = pl - 1; j > i; --j) {
+            v -= F.R[j * NP + i] * d[j];
+        }
+        d[i] = v / F.R[i * NP + i];
+    }
+    double* out { delta_par + static_cast<long long>(s) * NP };
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        out[k] = 0.0;
+    }
+    for (int a = 0; a < pg; ++a) {
+        out[idx_g[a]] = delta_g[a];
+    }
+    for (int i = 0; i < pl; ++i) {
+        out[idx_l[i]] = d[i];
+    }
+}
+
+// Local part of delta' D delta for delta1 and delta2 (lm_solver.cpp:388-393):
+// contrib[s] = [sum_local d2^2 D, sum_local d1^2 D]
+template <int NP>
+__global__ void k_acc_ratio_local(const unsigned* __restrict__ active,
+                                  const unsigned global_mask,
+                                  const int n_sets,
+                                  const double* __restrict__ dtd_local,
+                                  const double* __restrict__ delta1_par,
+                                  const double* __restrict__ delta2_par,
+                                  double* __restrict__ contrib)
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    const unsigned local { active[s] & ~global_mask };
+    double a2 { 0.0 };
+    double a1 { 0.0 };
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        if (((local >> k) & 1U) != 0U) {
+            const long long o { static_cast<long long>(s) * NP + k };
+            const double D { dtd_local[o] };
+            a2 += delta2_par[o] * (D * delta2_par[o]);
+            a1 += delta1_par[o] * (D * delta1_par[o]);
+        }
+    }
+    contrib[2 * s] = a2;
+    contrib[2 * s + 1] = a1;
+}
+
+// acc_ratio = sqrt(d2'Dd2 / d1'Dd1) > threshold => delta2 := 0
+// (lm_solver.cpp:394-397).  local_sums = all-reduced [a2, a1] of the local
+// blocks; the shared block is added here.
+__global__ void k_acc_ratio_final(const int pg,
+                                  const double threshold,
+                                  const double* __restrict__ local_sums,
+                                  const double* __restrict__ dtd_global,
+                                  const double* __restrict__ delta1_g,
+                                  const double* __restrict__ delta2_g,
+                                  LmState* __restrict__ state)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    double a2 { 0.0 };
+    double a1 { 0.0 };
+    for (int a = 0; a < pg; ++a) {
+        a2 += delta2_g[a] * (dtd_global[a] * delta2_g[a]);
+        a1 += delta1_g[a] * (dtd_global[a] * delta1_g[a]);
+    }
+    a2 += local_sums[0];
+    a1 += local_sums[1];
+    const double ratio { ::sqrt(a2 / a1) };
+    state->acc_ratio = ratio;
+    state->use_delta2 = ratio > threshold ? 0 : 1;
+}
+
+// saveParameters + updateParameters (lm_solver.cpp:192-204,230-253): beta +=
+// delta1, then (acceleration) beta -= 0.5 * delta2 as a second rounding step.
+__global__ void k_update_parameters(const long long n, // n_sets * NP
+                                    const int save,
+                                    const int accelerate,
+                                    const LmState* __restrict__ state,
+                                    const double* __restrict__ delta1_par,
+                                    const double* __restrict__ delta2_par,
+                                    double* __restrict__ par,
+                                    double* __restrict__ par_old)
+{
+    const long long i { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
+    if (i >= n) {
+        return;
+    }
+    double p { par[i] };
+    if (save != 0) {
+        par_old[i] = p;
+    }
+    p += delta1_par[i];
+    if (accelerate != 0 && state->use_delta2 != 0) {
+        p -= 0.5 * delta2_par[i];
+    }
+    par[i] = p;
+}
+
+// The accept / reject step of lm_solver.cpp:455-494 on the device
+__global__ void k_decide(const int lambda_incs,
+                         const double lambda_down,
+                         const double lambda_up,
+                         LmState* __restrict__ state,
+                         LmState* __restrict__ record) // pre-decision copy
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    LmState s { *state };
+    LmState rec { s };
+    if (s.new_chi2 < s.old_chi2) {
+        s.lambda /= lambda_down;
+        s.old_chi2 = s.new_chi2;
+        s.decision = 0;
+        s.i_lambda = 0;
+    } else if (s.i_lambda < lambda_incs) {
+        s.lambda *= lambda_up;
+        s.decision = 1;
+        s.i_lambda += 1;
+    } else {
+        s.decision = 2;
+        s.i_lambda = 0;
+    }
+    rec.decision = s.decision;
+    *state = s;
+    *record = rec;
+}
+
+// revertParameters (lm_solver.cpp:206-218), predicated on the device-side
+// decision so no host round trip sits between k_decide and the revert
+__global__ void k_revert_if_rejected(const long long n,
+                                     const LmState* __restrict__ state,
+                                     const double* __restrict__ par_old,
+                                     double* __restrict__ par)
+{
+    if (state->decision == 0) {
+        return;
+    }
+    const long long i { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
+    if (i < n) {
+        par[i] = par_old[i];
+    }
+}
+
+} // namespace gadfit_b200

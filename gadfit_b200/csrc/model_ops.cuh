@@ -1,0 +1,270 @@
+// Type-erased launchers: one instantiation of every kernel per registered
+// fitting function (the "model registry" of include/gadfit_b200/fit_models.h).
+#pragma once
+
+#include "block_arrow_kernels.cuh"
+#include "device_util.cuh"
+
+#include <memory>
+
+namespace gadfit_b200 {
+
+struct ModelOps
+{
+    virtual ~ModelOps() = default;
+    [[nodiscard]] virtual auto name() const -> const char* = 0;
+    [[nodiscard]] virtual auto n_pars() const -> int = 0;
+    // Resident CTAs per SM of each sweep kernel (0: chi2, 1: Jacobian, 2: omega)
+    [[nodiscard]] virtual auto ctas_per_sm(int which) const -> int = 0;
+    [[nodiscard]] virtual auto factor_bytes() const -> size_t = 0;
+    // First device use: opt in to the shared memory the Jacobian sweep needs
+    // and query occupancies (kept out of the constructor so that the host-side
+    // bookkeeping of the solver works without a GPU)
+    virtual auto init_device() -> void = 0;
+
+    virtual auto chi2(int grid, cudaStream_t st, const SweepArgs& a, double* partials) const
+      -> void = 0;
+    virtual auto jacobian(int grid,
+                          cudaStream_t st,
+                          const SweepArgs& a,
+                          int loss,
+                          const int* slot_base,
+                          double* partials,
+                          double* J_out,
+                          double* r_out,
+                          long long n_points) const -> void = 0;
+    virtual auto omega(int grid,
+                       cudaStream_t st,
+                       const SweepArgs& a,
+                       const double* seed,
+                       const double* J,
+                       long long n_points,
+                       const int* slot_base,
+                       double* partials,
+                       double* omega_out) const -> void = 0;
+    virtual auto value(cudaStream_t st, const double* par, double arg, double* out) const
+      -> void = 0;
+
+    virtual auto local_prepare(cudaStream_t st,
+                               const double* M,
+                               const unsigned* active,
+                               unsigned global_mask,
+                               int n_sets,
+                               int damp_max,
+                               double* dtd_local,
+                               double* contrib,
+                               int VG) const -> void = 0;
+    virtual auto local_schur(cudaStream_t st,
+                             const double* M,
+                             const unsigned* active,
+                             unsigned global_mask,
+                             int n_sets,
+                             const double* dtd_local,
+                             const LmState* state,
+                             void* factors,
+                             double* contrib,
+                             int VG) const -> void = 0;
+    virtual auto local_schur_rhs(cudaStream_t st,
+                                 const double* v_sets,
+                                 const unsigned* active,
+                                 unsigned global_mask,
+                                 int n_sets,
+                                 void* factors,
+                                 double* contrib,
+                                 int VG2) const -> void = 0;
+    virtual auto local_backsolve(cudaStream_t st,
+                                 const unsigned* active,
+                                 unsigned global_mask,
+                                 int n_sets,
+                                 const void* factors,
+                                 const double* delta_g,
+                                 double* delta_par) const -> void = 0;
+    virtual auto acc_ratio_local(cudaStream_t st,
+                                 const unsigned* active,
+                                 unsigned global_mask,
+                                 int n_sets,
+                                 const double* dtd_local,
+                                 const double* delta1_par,
+                                 const double* delta2_par,
+                                 double* contrib) const -> void = 0;
+};
+
+inline auto blocks_for(const long long n, const int threads) -> int
+{
+    return static_cast<int>((n + threads - 1) / threads);
+}
+
+template <class Model>
+struct ModelOpsImpl final : ModelOps
+{
+    static constexpr int NP { Model::n_pars };
+    using Shape = JacobianShape<Model>;
+    int occupancy[3] { 1, 1, 1 };
+    bool device_ready { false };
+
+    auto init_device() -> void override
+    {
+        static_assert(NP >= 1 && NP <= kMaxShared, "1..32 parameters supported");
+        if (device_ready) {
+            return;
+        }
+        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(Shape::smem_bytes)));
+        GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occupancy[0], k_chi2<Model>, kThreads, 0));
+        GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occupancy[1], k_jacobian<Model>, kThreads, Shape::smem_bytes));
+        GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occupancy[2], k_omega<Model>, kThreads, 0));
+        for (int& o : occupancy) {
+            o = o < 1 ? 1 : o;
+        }
+        device_ready = true;
+    }
+
+    [[nodiscard]] auto name() const -> const char* override { return Model::name; }
+    [[nodiscard]] auto n_pars() const -> int override { return NP; }
+    [[nodiscard]] auto ctas_per_sm(const int which) const -> int override
+    {
+        return occupancy[which];
+    }
+    [[nodiscard]] auto factor_bytes() const -> size_t override
+    {
+        return sizeof(LocalFactor<NP>);
+    }
+
+    auto chi2(const int grid, cudaStream_t st, const SweepArgs& a, double* partials) const
+      -> void override
+    {
+        k_chi2<Model><<<grid, kThreads, 0, st>>>(a, partials);
+    }
+    auto jacobian(const int grid,
+                  cudaStream_t st,
+                  const SweepArgs& a,
+                  const int loss,
+                  const int* slot_base,
+                  double* partials,
+                  double* J_out,
+                  double* r_out,
+                  const long long n_points) const -> void override
+    {
+        k_jacobian<Model><<<grid, kThreads, Shape::smem_bytes, st>>>(
+          a, loss, slot_base, partials, J_out, r_out, n_points);
+    }
+    auto omega(const int grid,
+               cudaStream_t st,
+               const SweepArgs& a,
+               const double* seed,
+               const double* J,
+               const long long n_points,
+               const int* slot_base,
+               double* partials,
+               double* omega_out) const -> void override
+    {
+        k_omega<Model><<<grid, kThreads, 0, st>>>(
+          a, seed, J, n_points, slot_base, partials, omega_out);
+    }
+    auto value(cudaStream_t st, const double* par, const double arg, double* out) const
+      -> void override
+    {
+        k_value<Model><<<1, 1, 0, st>>>(par, arg, out);
+    }
+
+    static constexpr int kSetThreads { 128 };
+
+    auto local_prepare(cudaStream_t st,
+                       const double* M,
+                       const unsigned* active,
+                       const unsigned global_mask,
+                       const int n_sets,
+                       const int damp_max,
+                       double* dtd_local,
+                       double* contrib,
+                       const int VG) const -> void override
+    {
+        k_local_prepare<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
+          M, active, global_mask, n_sets, damp_max, dtd_local, contrib, VG);
+    }
+    auto local_schur(cudaStream_t st,
+                     const double* M,
+                     const unsigned* active,
+                     const unsigned global_mask,
+                     const int n_sets,
+                     const double* dtd_local,
+                     const LmState* state,
+                     void* factors,
+                     double* contrib,
+                     const int VG) const -> void override
+    {
+        k_local_schur<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
+          M,
+          active,
+          global_mask,
+          n_sets,
+          dtd_local,
+          state,
+          static_cast<LocalFactor<NP>*>(factors),
+          contrib,
+          VG);
+    }
+    auto local_schur_rhs(cudaStream_t st,
+                         const double* v_sets,
+                         const unsigned* active,
+                         const unsigned global_mask,
+                         const int n_sets,
+                         void* factors,
+                         double* contrib,
+                         const int VG2) const -> void override
+    {
+        k_local_schur_rhs<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
+          v_sets,
+          active,
+          global_mask,
+          n_sets,
+          static_cast<LocalFactor<NP>*>(factors),
+          contrib,
+          VG2);
+    }
+    auto local_backsolve(cudaStream_t st,
+                         const unsigned* active,
+                         const unsigned global_mask,
+                         const int n_sets,
+                         const void* factors,
+                         const double* delta_g,
+                         double* delta_par) const -> void override
+    {
+        k_local_backsolve<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
+          active,
+          global_mask,
+          n_sets,
+          static_cast<const LocalFactor<NP>*>(factors),
+          delta_g,
+          delta_par);
+    }
+    auto acc_ratio_local(cudaStream_t st,
+                         const unsigned* active,
+                         const unsigned global_mask,
+                         const int n_sets,
+                         const double* dtd_local,
+                         const double* delta1_par,
+                         const double* delta2_par,
+                         double* contrib) const -> void override
+    {
+        k_acc_ratio_local<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
+          active, global_mask, n_sets, dtd_local, delta1_par, delta2_par, contrib);
+    }
+};
+
+inline auto make_model_ops(const char* model_name) -> std::unique_ptr<ModelOps>
+{
+    std::unique_ptr<ModelOps> ops;
+    models::for_each_model([&]<class Model>() {
+        if (!ops && std::string { model_name } == Model::name) {
+            ops = std::make_unique<ModelOpsImpl<Model>>();
+        }
+    });
+    return ops;
+}
+
+} // namespace gadfit_b200

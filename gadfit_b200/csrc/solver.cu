@@ -1,0 +1,1621 @@
+// Host side of the B200-native LM solver + the C-ABI of include/gadfit_b200.h.
+//
+// Thin by design: bookkeeping that the reference does in LMsolver
+// (c++/gadfit/lm_solver.cpp) -- data set / parameter registration, the
+// Jacobian column map, the order of the phases of fit() -- lives here; every
+// floating point operation of the fit runs in the kernels of
+// sweep_kernels.cuh and block_arrow_kernels.cuh.  The LM state (lambda, chi2,
+// accept/reject decision) is device resident; the host reads one small record
+// per trial step to know which phase to launch next and to keep the trace.
+
+#include "model_ops.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace gadfit_b200 {
+
+namespace {
+
+constexpr size_t kDenseLimit { size_t { 1 } << 27 };
+
+struct Partition
+{
+    int first { 0 };
+    int end { 0 };
+    bool split { false };
+};
+
+// Whole data sets per rank, balanced by points; with fewer data sets than
+// ranks every rank takes a slice of the points of every data set (the
+// img_bounds idea of fortran/gadfit/gadfit.F90:539-551)
+auto compute_partition(const int n_sets, const int* n_points, const int rank, const int world)
+  -> Partition
+{
+    if (world <= 1) {
+        return { 0, n_sets, false };
+    }
+    if (n_sets < world) {
+        return { 0, n_sets, true };
+    }
+    long long total { 0 };
+    for (int s = 0; s < n_sets; ++s) {
+        total += n_points[s];
+    }
+    Partition part { n_sets, n_sets, false };
+    long long prefix { 0 };
+    bool found { false };
+    for (int s = 0; s < n_sets; ++s) {
+        int owner { 0 };
+        if (total > 0) {
+            const long double mid { static_cast<long double>(prefix)
+                                    + 0.5L * static_cast<long double>(n_points[s]) };
+            owner = static_cast<int>(mid * world / static_cast<long double>(total));
+        } else {
+            owner = static_cast<int>(static_cast<long long>(s) * world / n_sets);
+        }
+        owner = std::min(owner, world - 1);
+        if (owner == rank) {
+            if (!found) {
+                part.first = s;
+                found = true;
+            }
+            part.end = s + 1;
+        }
+        prefix += n_points[s];
+    }
+    if (!found) {
+        part.first = part.end = 0;
+    }
+    return part;
+}
+
+__global__ void k_fill(double* p, const long long n, const double v)
+{
+    const long long i { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
+    if (i < n) {
+        p[i] = v;
+    }
+}
+
+__global__ void k_copy_chi2_to_old(LmState* state)
+{
+    state->old_chi2 = state->new_chi2;
+}
+
+// Dense symmetric inverse through the Cholesky factor (LMsolver::getInvJTJ,
+// lm_solver.cpp:578-585 = dpptrf + dpotri).  Small n only, one thread.
+__global__ void k_dense_inverse(const int n, const double* A, double* L, double* inv)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < i; ++j) {
+            double v { A[i * n + j] };
+            for (int k = 0; k < j; ++k) {
+                v -= L[i * n + k] * L[j * n + k];
+            }
+            L[i * n + j] = v / L[j * n + j];
+        }
+        double v { A[i * n + i] };
+        for (int k = 0; k < i; ++k) {
+            v -= L[i * n + k] * L[i * n + k];
+        }
+        L[i * n + i] = ::sqrt(v);
+    }
+    for (int c = 0; c < n; ++c) {
+        // Solve L L' x = e_c; y is stored in column c of inv
+        for (int i = 0; i < n; ++i) {
+            double v { i == c ? 1.0 : 0.0 };
+            for (int j = 0; j < i; ++j) {
+                v -= L[i * n + j] * inv[j * n + c];
+            }
+            inv[i * n + c] = v / L[i * n + i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double v { inv[i * n + c] };
+            for (int j = n - 1; j > i; --j) {
+                v -= L[j * n + i] * inv[j * n + c];
+            }
+            inv[i * n + c] = v / L[i * n + i];
+        }
+    }
+}
+
+struct SlotTable
+{
+    int grid { 0 };
+    int n_slots { 0 };
+    DeviceBuffer<int> base;  // [grid]  first slot of each CTA
+    DeviceBuffer<int> first; // [n_sets] first slot of each data set
+    DeviceBuffer<int> count; // [n_sets]
+};
+
+} // namespace
+
+// State and phases of one solver; the opaque C handle derives from it
+struct SolverImpl
+{
+    // ---- problem description (host; mirrors the private state of LMsolver,
+    // lm_solver.h:101-123)
+    struct DataSet
+    {
+        int n;
+        const double* x;
+        const double* y;
+        const double* errors;
+    };
+    std::unique_ptr<ModelOps> ops;
+    int NP { 0 };
+    std::vector<DataSet> sets;
+    std::vector<double> par;         // [S][NP]
+    std::vector<int> n_set_pars;     // FitFunction::getNumPars per data set
+    std::vector<unsigned> active;    // Indices::active as bit masks
+    unsigned global_mask { 0U };     // Indices::global
+    std::vector<std::string> names;
+    bool set_par_called { false };
+    gadfit_b200_settings settings {};
+    std::vector<double> DTD_min;
+    std::string last_error;
+
+    // ---- indexing (prepareIndexing, lm_solver.cpp:119-190)
+    long long n_active { 0 };
+    long long n_datapoints { 0 };
+    int dof { 0 };
+    int pg { 0 };
+    std::vector<int> global_pars;       // model parameter of global column a
+    std::vector<long long> local_off;   // first local column of data set s
+
+    // ---- device
+    int device { 0 };
+    cudaStream_t stream { nullptr };
+    bool device_ready { false };
+    bool data_uploaded { false };
+    long long n_launches { 0 };
+
+    // communicator
+    int rank { 0 };
+    int world { 1 };
+    ncclComm_t comm { nullptr };
+
+    // this rank's share of the problem
+    Partition part {};
+    int n_local_sets { 0 };
+    long long n_local_points { 0 };
+    std::vector<long long> local_begin; // first owned point of each local set
+    std::vector<long long> local_count; // owned points of each local set
+
+    DeviceBuffer<double> d_x, d_y, d_sig;
+    DeviceBuffer<int> d_tile_set, d_tile_len;
+    DeviceBuffer<long long> d_tile_off;
+    std::vector<int> h_tile_set;
+    int n_tiles { 0 };
+    SlotTable slots_jac, slots_omega;
+    int grid_chi2 { 0 };
+
+    DeviceBuffer<double> d_par, d_par_old, d_par_jac;
+    DeviceBuffer<unsigned> d_active;
+    DeviceBuffer<double> d_chi2_partials, d_jac_partials, d_omega_partials;
+    DeviceBuffer<double> d_M;      // [n_local_sets][NT]
+    DeviceBuffer<double> d_vsets;  // [n_local_sets][NP]  J^T omega by parameter
+    DeviceBuffer<double> d_dtd_local, d_dtd_global;
+    DeviceBuffer<double> d_contrib, d_stage;
+    DeviceBuffer<double> d_shared_sums, d_schur_sums, d_rhs2_sums, d_ratio_sums;
+    DeviceBuffer<double> d_chol, d_delta1_g, d_delta2_g;
+    DeviceBuffer<double> d_delta1_par, d_delta2_par;
+    DeviceBuffer<unsigned char> d_factors;
+    DeviceBuffer<double> d_J, d_resid, d_omega;
+    DeviceBuffer<LmState> d_state;  // [0] live state, [1] record, [2] copy
+    DeviceBuffer<double> d_scratch;
+    LmState* h_mirror { nullptr };  // pinned, 2 entries: record, state
+    double* h_scalar { nullptr };   // pinned
+
+    // ---- results of the last fit
+    std::vector<gadfit_b200_trial> trace;
+    int n_iterations { 0 };
+    bool fitted { false };
+    double lambda_lhs { 0.0 };      // lambda of the last left-hand side
+    bool have_delta2 { false };
+    PhaseTimer t_jacobian, t_chi2, t_linalg, t_omega, t_main, t_jac_kernel;
+
+    ~SolverImpl()
+    {
+        if (comm != nullptr) {
+            Nccl::instance().commDestroy(comm);
+        }
+        if (h_mirror != nullptr) {
+            cudaFreeHost(h_mirror);
+        }
+        if (h_scalar != nullptr) {
+            cudaFreeHost(h_scalar);
+        }
+        if (stream != nullptr) {
+            cudaStreamDestroy(stream);
+        }
+    }
+
+    // ------------------------------------------------------------ host logic
+
+    auto add_dataset(const int n, const double* x, const double* y, const double* e) -> void
+    {
+        // lm_solver.cpp:35-37
+        if (set_par_called) {
+            throw StatusError { GADFIT_B200_LATE_ADD_DATASET_CALL,
+                                "addDataset called after setPar" };
+        }
+        if (n < 0) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "negative number of points" };
+        }
+        sets.push_back({ n, x, y, e });
+        par.resize(sets.size() * NP, 0.0);
+        n_set_pars.push_back(0);
+        // A new data set starts as a copy of the fitting function of the
+        // last one (lm_solver.cpp:52-54); parameters cannot have been set yet
+        active.push_back(0U);
+        data_uploaded = false;
+    }
+
+    auto set_par(const int i_par, const double val, const bool is_active, const int i_dataset)
+      -> void
+    {
+        // lm_solver.cpp:65-68
+        const int S { static_cast<int>(sets.size()) };
+        if (i_dataset >= S || S == 0) {
+            throw StatusError { GADFIT_B200_SET_PAR_INVALID_INDEX,
+                                "invalid data set index " + std::to_string(i_dataset) };
+        }
+        if (i_par < 0 || i_par >= NP || i_dataset < -1) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT,
+                                "parameter index outside the fitting function" };
+        }
+        set_par_called = true;
+        const unsigned bit { 1U << i_par };
+        if (i_dataset == -1) {
+            // lm_solver.cpp:73-88
+            if (is_active) {
+                global_mask |= bit;
+            } else {
+                global_mask &= ~bit;
+            }
+            for (int s = 0; s < S; ++s) {
+                par[static_cast<size_t>(s) * NP + i_par] = val;
+                n_set_pars[s] = std::max(n_set_pars[s], i_par + 1);
+                active[s] = is_active ? (active[s] | bit) : (active[s] & ~bit);
+            }
+        } else {
+            // lm_solver.cpp:89-98
+            global_mask &= ~bit;
+            par[static_cast<size_t>(i_dataset) * NP + i_par] = val;
+            n_set_pars[i_dataset] = std::max(n_set_pars[i_dataset], i_par + 1);
+            active[i_dataset] =
+              is_active ? (active[i_dataset] | bit) : (active[i_dataset] & ~bit);
+        }
+    }
+
+    // lm_solver.cpp:119-190, same order of checks
+    auto prepare_indexing() -> void
+    {
+        const int S { static_cast<int>(sets.size()) };
+        if (S == 0) {
+            throw StatusError { GADFIT_B200_NO_FITTING_PARAMETERS, "no data sets" };
+        }
+        n_active = 0;
+        for (const unsigned a : active) {
+            n_active += popcount32(a);
+        }
+        n_active -= static_cast<long long>(S - 1) * popcount32(global_mask);
+        if (n_active > 0 && S > 1 && global_mask == 0U) {
+            throw StatusError { GADFIT_B200_NO_GLOBAL_PARAMETERS,
+                                "several data sets but no global fitting parameter" };
+        }
+        n_datapoints = 0;
+        for (const auto& set : sets) {
+            n_datapoints += set.n;
+        }
+        const long long degrees { n_datapoints - n_active };
+        if (degrees < 0) {
+            throw StatusError { GADFIT_B200_NEGATIVE_DEGREES_OF_FREEDOM,
+                                "more fitting parameters than data points" };
+        }
+        // No degrees of freedom: chi2/DOF has no meaning (lm_solver.cpp:140-144)
+        dof = degrees == 0 ? 1 : static_cast<int>(std::min<long long>(degrees, INT32_MAX));
+        for (const int n : n_set_pars) {
+            if (n != n_set_pars.front()) {
+                throw StatusError { GADFIT_B200_UNINITIALIZED_PARAMETER,
+                                    "a parameter is not set for every data set" };
+            }
+        }
+        if (n_set_pars.front() != NP) {
+            throw StatusError { GADFIT_B200_UNINITIALIZED_PARAMETER,
+                                "the fitting function has " + std::to_string(NP)
+                                  + " parameters" };
+        }
+        // Column map: globals first in ascending parameter index, then the
+        // locals of data set 0, 1, ... (lm_solver.cpp:155-186)
+        global_pars.clear();
+        for (int k = 0; k < NP; ++k) {
+            if (((global_mask >> k) & 1U) != 0U) {
+                global_pars.push_back(k);
+            }
+        }
+        pg = static_cast<int>(global_pars.size());
+        local_off.resize(S);
+        long long next { pg };
+        for (int s = 0; s < S; ++s) {
+            local_off[s] = next;
+            next += popcount32(active[s] & ~global_mask);
+        }
+        if (n_active == 0) {
+            throw StatusError { GADFIT_B200_NO_FITTING_PARAMETERS,
+                                "no active fitting parameters" };
+        }
+    }
+
+    // Column of parameter k of data set s, -1 if passive
+    [[nodiscard]] auto column(const int s, const int k) const -> long long
+    {
+        const unsigned bit { 1U << k };
+        if ((active[s] & bit) == 0U) {
+            return -1;
+        }
+        if ((global_mask & bit) != 0U) {
+            return slot_of(global_mask, k);
+        }
+        return local_off[s] + slot_of(active[s] & ~global_mask, k);
+    }
+
+    // ---------------------------------------------------------- device setup
+
+    auto launched(const int n = 1) -> void
+    {
+        n_launches += n;
+        GADFIT_CUDA_TRY(cudaGetLastError());
+    }
+
+    auto ensure_device() -> void
+    {
+        GADFIT_CUDA_TRY(cudaSetDevice(device));
+        if (device_ready) {
+            return;
+        }
+        GADFIT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        GADFIT_CUDA_TRY(cudaMallocHost(&h_mirror, 2 * sizeof(LmState)));
+        GADFIT_CUDA_TRY(cudaMallocHost(&h_scalar, 8 * sizeof(double)));
+        ops->init_device();
+        d_state.ensure(3);
+        d_scratch.ensure(8);
+        device_ready = true;
+    }
+
+    auto sm_count() const -> int
+    {
+        int n { 0 };
+        GADFIT_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+        return n;
+    }
+
+    auto all_reduce(double* buf, const size_t n) -> void
+    {
+        if (world <= 1 || n == 0) {
+            return;
+        }
+        auto& nccl { Nccl::instance() };
+        nccl.check(nccl.allReduce(buf, buf, n, ncclDouble, ncclSum, comm, stream),
+                   "ncclAllReduce");
+    }
+
+    auto build_slots(SlotTable& table, const int grid) -> void
+    {
+        table.grid = grid;
+        std::vector<int> base(std::max(grid, 1), 0);
+        std::vector<int> first(std::max(n_local_sets, 1), 0);
+        std::vector<int> count(std::max(n_local_sets, 1), 0);
+        int slot { 0 };
+        for (int b = 0; b < grid; ++b) {
+            const int t0 { static_cast<int>(static_cast<long long>(n_tiles) * b / grid) };
+            const int t1 { static_cast<int>(static_cast<long long>(n_tiles) * (b + 1)
+                                            / grid) };
+            base[b] = slot;
+            int cur { -1 };
+            for (int t = t0; t < t1; ++t) {
+                const int s { h_tile_set[t] };
+                if (s != cur) {
+                    if (count[s] == 0) {
+                        first[s] = slot;
+                    }
+                    ++count[s];
+                    ++slot;
+                    cur = s;
+                }
+            }
+        }
+        table.n_slots = slot;
+        table.base.upload(base, stream);
+        table.first.upload(first, stream);
+        table.count.upload(count, stream);
+        // The host vectors die at scope exit; the copies are from pageable
+        // memory and therefore already staged by the runtime
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    // Copy this rank's share of the data sets to HBM, concatenated data-set
+    // major, and lay out the tiles.
+    auto upload_data() -> void
+    {
+        ensure_device();
+        const int S { static_cast<int>(sets.size()) };
+        std::vector<int> n_points(S);
+        for (int s = 0; s < S; ++s) {
+            n_points[s] = sets[s].n;
+        }
+        part = compute_partition(S, n_points.data(), rank, world);
+        n_local_sets = part.end - part.first;
+        local_begin.assign(n_local_sets, 0);
+        local_count.assign(n_local_sets, 0);
+        n_local_points = 0;
+        for (int ls = 0; ls < n_local_sets; ++ls) {
+            const long long n { sets[part.first + ls].n };
+            if (part.split) {
+                local_begin[ls] = n * rank / world;
+                local_count[ls] = n * (rank + 1) / world - local_begin[ls];
+            } else {
+                local_count[ls] = n;
+            }
+            n_local_points += local_count[ls];
+        }
+        d_x.ensure(n_local_points);
+        d_y.ensure(n_local_points);
+        d_sig.ensure(n_local_points);
+        // Merge host-contiguous data sets into single copies
+        const auto copy_field { [&](const int field, double* dst) {
+            long long off { 0 };
+            int ls { 0 };
+            while (ls < n_local_sets) {
+                const auto field_ptr { [&](const int l) -> const double* {
+                    const auto& set { sets[part.first + l] };
+                    const double* p { field == 0 ? set.x
+                                                 : (field == 1 ? set.y : set.errors) };
+                    return p == nullptr ? nullptr : p + local_begin[l];
+                } };
+                const double* start { field_ptr(ls) };
+                long long run { local_count[ls] };
+                int next { ls + 1 };
+                if (start != nullptr) {
+                    while (next < n_local_sets && field_ptr(next) == start + run) {
+                        run += local_count[next];
+                        ++next;
+                    }
+                }
+                if (run > 0) {
+                    if (start == nullptr) {
+                        if (field != 2) {
+                            throw StatusError {
+                                GADFIT_B200_INVALID_ARGUMENT,
+                                "data set " + std::to_string(part.first + ls)
+                                  + " is owned by this rank but has no data"
+                            };
+                        }
+                        // Equal weights by default (lm_solver.cpp:43-48)
+                        k_fill<<<blocks_for(run, 256), 256, 0, stream>>>(dst + off, run, 1.0);
+                        launched();
+                    } else {
+                        GADFIT_CUDA_TRY(cudaMemcpyAsync(dst + off,
+                                                        start,
+                                                        run * sizeof(double),
+                                                        cudaMemcpyHostToDevice,
+                                                        stream));
+                    }
+                }
+                off += run;
+                ls = next;
+            }
+        } };
+        copy_field(0, d_x.ptr);
+        copy_field(1, d_y.ptr);
+        copy_field(2, d_sig.ptr);
+
+        // Tiles
+        h_tile_set.clear();
+        std::vector<long long> tile_off;
+        std::vector<int> tile_len;
+        long long off { 0 };
+        for (int ls = 0; ls < n_local_sets; ++ls) {
+            for (long long p = 0; p < local_count[ls]; p += kTile) {
+                h_tile_set.push_back(ls);
+                tile_off.push_back(off + p);
+                tile_len.push_back(static_cast<int>(std::min<long long>(kTile, local_count[ls] - p)));
+            }
+            off += local_count[ls];
+        }
+        n_tiles = static_cast<int>(h_tile_set.size());
+        d_tile_set.upload(h_tile_set, stream);
+        d_tile_off.upload(tile_off, stream);
+        d_tile_len.upload(tile_len, stream);
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+
+        const int sms { sm_count() };
+        const auto grid_for { [&](const int which) {
+            return std::max(1, std::min(n_tiles, sms * ops->ctas_per_sm(which)));
+        } };
+        grid_chi2 = grid_for(0);
+        d_chi2_partials.ensure(grid_chi2);
+        build_slots(slots_jac, grid_for(1));
+        build_slots(slots_omega, grid_for(2));
+        const int NA { NP + 1 };
+        const int NT { NA * (NA + 1) / 2 };
+        d_jac_partials.ensure(static_cast<size_t>(std::max(slots_jac.n_slots, 1)) * NT);
+        d_omega_partials.ensure(static_cast<size_t>(std::max(slots_omega.n_slots, 1)) * NP);
+        d_M.zero(static_cast<size_t>(std::max(n_local_sets, 1)) * NT, stream);
+        d_vsets.zero(static_cast<size_t>(std::max(n_local_sets, 1)) * NP, stream);
+        data_uploaded = true;
+    }
+
+    // Parameters and roles of the local data sets -> device
+    auto upload_parameters() -> void
+    {
+        if (!data_uploaded) {
+            upload_data();
+        }
+        const size_t n { static_cast<size_t>(n_local_sets) * NP };
+        d_par.upload(par.data() + static_cast<size_t>(part.first) * NP, n, stream);
+        d_par_old.ensure(n);
+        d_par_jac.ensure(n);
+        d_active.upload(active.data() + part.first, n_local_sets, stream);
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    auto download_parameters() -> void
+    {
+        const size_t n { static_cast<size_t>(n_local_sets) * NP };
+        if (world > 1 && !part.split) {
+            // Every rank ends up with the parameters of every data set: each
+            // fills its block of a zeroed [S][NP] array, summed over ranks
+            const size_t all { sets.size() * static_cast<size_t>(NP) };
+            d_stage.zero(all, stream);
+            if (n > 0) {
+                GADFIT_CUDA_TRY(cudaMemcpyAsync(d_stage.ptr
+                                                  + static_cast<size_t>(part.first) * NP,
+                                                d_par.ptr,
+                                                n * sizeof(double),
+                                                cudaMemcpyDeviceToDevice,
+                                                stream));
+            }
+            all_reduce(d_stage.ptr, all);
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(par.data(),
+                                            d_stage.ptr,
+                                            all * sizeof(double),
+                                            cudaMemcpyDeviceToHost,
+                                            stream));
+        } else if (n > 0) {
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(par.data() + static_cast<size_t>(part.first) * NP,
+                                            d_par.ptr,
+                                            n * sizeof(double),
+                                            cudaMemcpyDeviceToHost,
+                                            stream));
+        }
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    [[nodiscard]] auto sweep_args() const -> SweepArgs
+    {
+        return { d_x.ptr,        d_y.ptr,        d_sig.ptr, d_tile_set.ptr,
+                 d_tile_off.ptr, d_tile_len.ptr, n_tiles,   d_par.ptr };
+    }
+
+    // --------------------------------------------------------------- phases
+
+    // chi2 at the current parameters -> *dst (device), summed over ranks
+    auto chi2_phase(double* dst) -> void
+    {
+        t_chi2.start(stream);
+        if (n_tiles > 0) {
+            ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr);
+            launched();
+            k_sum_partials<<<1, kThreads, 0, stream>>>(d_chi2_partials.ptr, grid_chi2, dst);
+            launched();
+        } else {
+            GADFIT_CUDA_TRY(cudaMemsetAsync(dst, 0, sizeof(double), stream));
+        }
+        all_reduce(dst, 1);
+        t_chi2.stop(stream);
+    }
+
+    // Deterministic column sums of contrib[n_local_sets][V] -> dst[V]
+    auto column_sums(const double* contrib, const int V, double* dst) -> void
+    {
+        if (V == 0) {
+            return;
+        }
+        if (n_local_sets == 0) {
+            GADFIT_CUDA_TRY(cudaMemsetAsync(dst, 0, V * sizeof(double), stream));
+            return;
+        }
+        constexpr int chunk { 64 };
+        const int blocks { (n_local_sets + chunk - 1) / chunk };
+        const int threads { std::min(256, ((V + 31) / 32) * 32) };
+        if (blocks == 1) {
+            k_column_sums<<<1, threads, 0, stream>>>(contrib, n_local_sets, V, chunk, dst);
+            launched();
+            return;
+        }
+        d_stage.ensure(std::max(d_stage.capacity, static_cast<size_t>(blocks) * V));
+        k_column_sums<<<blocks, threads, 0, stream>>>(contrib, n_local_sets, V, chunk, d_stage.ptr);
+        k_column_sums<<<1, threads, 0, stream>>>(d_stage.ptr, blocks, V, blocks, dst);
+        launched(2);
+    }
+
+    [[nodiscard]] auto shared_len() const -> int { return pg * (pg + 1) / 2 + pg; }
+
+    // computeLeftHandSide + computeRightHandSide (lm_solver.cpp:286-346)
+    auto jacobian_phase(const bool store_rows, const bool store_residuals) -> void
+    {
+        const int NA { NP + 1 };
+        const int NT { NA * (NA + 1) / 2 };
+        t_jacobian.start(stream);
+        const size_t n_par { static_cast<size_t>(n_local_sets) * NP };
+        if (n_par > 0) {
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par_jac.ptr,
+                                            d_par.ptr,
+                                            n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice,
+                                            stream));
+        }
+        if (n_tiles > 0) {
+            if (store_rows) {
+                d_J.ensure(static_cast<size_t>(NP) * n_local_points);
+            }
+            if (store_residuals) {
+                d_resid.ensure(n_local_points);
+            }
+            t_jac_kernel.start(stream);
+            ops->jacobian(slots_jac.grid,
+                          stream,
+                          sweep_args(),
+                          settings.loss,
+                          slots_jac.base.ptr,
+                          d_jac_partials.ptr,
+                          store_rows ? d_J.ptr : nullptr,
+                          store_residuals ? d_resid.ptr : nullptr,
+                          n_local_points);
+            t_jac_kernel.stop(stream);
+            launched();
+            k_reduce_slots<<<blocks_for(static_cast<long long>(n_local_sets) * NT, 256),
+                             256,
+                             0,
+                             stream>>>(d_jac_partials.ptr,
+                                       slots_jac.first.ptr,
+                                       slots_jac.count.ptr,
+                                       n_local_sets,
+                                       NT,
+                                       d_M.ptr);
+            launched();
+        }
+        if (part.split) {
+            all_reduce(d_M.ptr, static_cast<size_t>(n_local_sets) * NT);
+        }
+        t_jacobian.stop(stream);
+
+        t_linalg.start(stream);
+        const int VG { shared_len() };
+        d_contrib.ensure(static_cast<size_t>(std::max(n_local_sets, 1)) * std::max(VG, 2));
+        d_shared_sums.ensure(std::max(VG, 1));
+        if (n_local_sets > 0) {
+            ops->local_prepare(stream,
+                               d_M.ptr,
+                               d_active.ptr,
+                               global_mask,
+                               n_local_sets,
+                               settings.damp_max,
+                               d_dtd_local.ptr,
+                               d_contrib.ptr,
+                               VG);
+            launched();
+        }
+        column_sums(d_contrib.ptr, VG, d_shared_sums.ptr);
+        if (!part.split) {
+            all_reduce(d_shared_sums.ptr, VG);
+        }
+        t_linalg.stop(stream);
+    }
+
+    // computeDeltas (lm_solver.cpp:348-399) followed by updateParameters
+    auto solve_phase(const bool first_trial) -> void
+    {
+        const int VG { shared_len() };
+        const bool accelerate { settings.acceleration_threshold > 0.0 };
+        t_linalg.start(stream);
+        d_schur_sums.ensure(std::max(VG, 1));
+        if (n_local_sets > 0) {
+            ops->local_schur(stream,
+                             d_M.ptr,
+                             d_active.ptr,
+                             global_mask,
+                             n_local_sets,
+                             d_dtd_local.ptr,
+                             d_state.ptr,
+                             d_factors.ptr,
+                             d_contrib.ptr,
+                             VG);
+            launched();
+        }
+        column_sums(d_contrib.ptr, VG, d_schur_sums.ptr);
+        if (!part.split) {
+            all_reduce(d_schur_sums.ptr, VG);
+        }
+        if (pg > 0) {
+            k_shared_solve<<<1, 32, 0, stream>>>(pg,
+                                                 1,
+                                                 first_trial ? 1 : 0,
+                                                 settings.damp_max,
+                                                 d_shared_sums.ptr,
+                                                 d_schur_sums.ptr,
+                                                 nullptr,
+                                                 d_state.ptr,
+                                                 d_dtd_global.ptr,
+                                                 d_chol.ptr,
+                                                 d_delta1_g.ptr);
+            launched();
+        }
+        if (n_local_sets > 0) {
+            ops->local_backsolve(stream,
+                                 d_active.ptr,
+                                 global_mask,
+                                 n_local_sets,
+                                 d_factors.ptr,
+                                 d_delta1_g.ptr,
+                                 d_delta1_par.ptr);
+            launched();
+        }
+        t_linalg.stop(stream);
+
+        if (accelerate) {
+            // omega sweep along delta1 (lm_solver.cpp:361-381)
+            t_omega.start(stream);
+            if (n_tiles > 0) {
+                ops->omega(slots_omega.grid,
+                           stream,
+                           sweep_args(),
+                           d_delta1_par.ptr,
+                           d_J.ptr,
+                           n_local_points,
+                           slots_omega.base.ptr,
+                           d_omega_partials.ptr,
+                           nullptr);
+                launched();
+                k_reduce_slots<<<blocks_for(static_cast<long long>(n_local_sets) * NP, 256),
+                                 256,
+                                 0,
+                                 stream>>>(d_omega_partials.ptr,
+                                           slots_omega.first.ptr,
+                                           slots_omega.count.ptr,
+                                           n_local_sets,
+                                           NP,
+                                           d_vsets.ptr);
+                launched();
+            }
+            if (part.split) {
+                all_reduce(d_vsets.ptr, static_cast<size_t>(n_local_sets) * NP);
+            }
+            t_omega.stop(stream);
+
+            // delta2 with the same factor (lm_solver.cpp:383-384)
+            t_linalg.start(stream);
+            d_rhs2_sums.ensure(std::max(2 * pg, 1));
+            d_ratio_sums.ensure(2);
+            if (n_local_sets > 0) {
+                ops->local_schur_rhs(stream,
+                                     d_vsets.ptr,
+                                     d_active.ptr,
+                                     global_mask,
+                                     n_local_sets,
+                                     d_factors.ptr,
+                                     d_contrib.ptr,
+                                     2 * pg);
+                launched();
+            }
+            column_sums(d_contrib.ptr, 2 * pg, d_rhs2_sums.ptr);
+            if (!part.split) {
+                all_reduce(d_rhs2_sums.ptr, 2 * pg);
+            }
+            if (pg > 0) {
+                k_shared_solve<<<1, 32, 0, stream>>>(pg,
+                                                     2,
+                                                     0,
+                                                     settings.damp_max,
+                                                     d_shared_sums.ptr,
+                                                     d_schur_sums.ptr,
+                                                     d_rhs2_sums.ptr,
+                                                     d_state.ptr,
+                                                     d_dtd_global.ptr,
+                                                     d_chol.ptr,
+                                                     d_delta2_g.ptr);
+                launched();
+            }
+            if (n_local_sets > 0) {
+                ops->local_backsolve(stream,
+                                     d_active.ptr,
+                                     global_mask,
+                                     n_local_sets,
+                                     d_factors.ptr,
+                                     d_delta2_g.ptr,
+                                     d_delta2_par.ptr);
+                ops->acc_ratio_local(stream,
+                                     d_active.ptr,
+                                     global_mask,
+                                     n_local_sets,
+                                     d_dtd_local.ptr,
+                                     d_delta1_par.ptr,
+                                     d_delta2_par.ptr,
+                                     d_contrib.ptr);
+                launched(2);
+            }
+            column_sums(d_contrib.ptr, 2, d_ratio_sums.ptr);
+            if (!part.split) {
+                all_reduce(d_ratio_sums.ptr, 2);
+            }
+            k_acc_ratio_final<<<1, 32, 0, stream>>>(pg,
+                                                    settings.acceleration_threshold,
+                                                    d_ratio_sums.ptr,
+                                                    d_dtd_global.ptr,
+                                                    d_delta1_g.ptr,
+                                                    d_delta2_g.ptr,
+                                                    d_state.ptr);
+            launched();
+            t_linalg.stop(stream);
+            have_delta2 = true;
+        }
+
+        // saveParameters (first trial only) + updateParameters
+        const long long n_par { static_cast<long long>(n_local_sets) * NP };
+        if (n_par > 0) {
+            k_update_parameters<<<blocks_for(n_par, 256), 256, 0, stream>>>(
+              n_par,
+              first_trial ? 1 : 0,
+              accelerate ? 1 : 0,
+              d_state.ptr,
+              d_delta1_par.ptr,
+              d_delta2_par.ptr,
+              d_par.ptr,
+              d_par_old.ptr);
+            launched();
+        }
+    }
+
+    // The initial values of the damping matrix (lm_solver.cpp:414,424-428)
+    auto init_damping() -> void
+    {
+        const size_t n_loc { static_cast<size_t>(std::max(n_local_sets, 1)) * NP };
+        std::vector<double> dtd_local(n_loc, 0.0);
+        std::vector<double> dtd_global(std::max(pg, 1), 0.0);
+        if (DTD_min.size() > 1) {
+            if (static_cast<long long>(DTD_min.size()) < n_active) {
+                throw StatusError { GADFIT_B200_INVALID_ARGUMENT,
+                                    "DTD_min is shorter than the number of active "
+                                    "parameters" };
+            }
+            for (int a = 0; a < pg; ++a) {
+                dtd_global[a] = DTD_min[a];
+            }
+            for (int ls = 0; ls < n_local_sets; ++ls) {
+                const int s { part.first + ls };
+                for (int k = 0; k < NP; ++k) {
+                    const long long col { column(s, k) };
+                    if (col >= pg) {
+                        dtd_local[static_cast<size_t>(ls) * NP + k] = DTD_min[col];
+                    }
+                }
+            }
+        }
+        d_dtd_local.upload(dtd_local, stream);
+        d_dtd_global.upload(dtd_global, stream);
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    auto reset_timers() -> void
+    {
+        for (PhaseTimer* t :
+             { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
+            t->reset();
+        }
+    }
+
+    // LMsolver::fit, lm_solver.cpp:401-511
+    auto fit(const double lambda0) -> void
+    {
+        prepare_indexing();
+        ensure_device();
+        upload_parameters();
+        reset_timers();
+        init_damping();
+        const size_t n_par { static_cast<size_t>(std::max(n_local_sets, 1)) * NP };
+        d_delta1_par.zero(n_par, stream);
+        d_delta2_par.zero(n_par, stream);
+        d_delta1_g.zero(kMaxShared, stream);
+        d_delta2_g.zero(kMaxShared, stream);
+        d_chol.ensure(kMaxShared * kMaxShared);
+        d_factors.ensure(static_cast<size_t>(std::max(n_local_sets, 1)) * ops->factor_bytes());
+        const bool accelerate { settings.acceleration_threshold > 0.0 };
+        have_delta2 = false;
+        trace.clear();
+        n_iterations = 0;
+
+        LmState init {};
+        init.lambda = lambda0;
+        init.use_delta2 = 0;
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(
+          d_state.ptr, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        lambda_lhs = lambda0;
+        double lambda { lambda0 };
+
+        t_main.start(stream);
+        chi2_phase(&d_state.ptr->new_chi2);
+        k_copy_chi2_to_old<<<1, 1, 0, stream>>>(d_state.ptr);
+        launched();
+        int i_iteration { 0 };
+        bool finished { settings.iteration_limit == 0 };
+        while (!finished) {
+            ++i_iteration;
+            jacobian_phase(accelerate, false);
+            lambda_lhs = lambda;
+            solve_phase(true);
+            for (int i_lambda = 0; i_lambda <= settings.lambda_incs; ++i_lambda) {
+                chi2_phase(&d_state.ptr->new_chi2);
+                k_decide<<<1, 1, 0, stream>>>(settings.lambda_incs,
+                                              settings.lambda_down,
+                                              settings.lambda_up,
+                                              d_state.ptr,
+                                              d_state.ptr + 1);
+                const long long n { static_cast<long long>(n_local_sets) * NP };
+                if (n > 0) {
+                    k_revert_if_rejected<<<blocks_for(n, 256), 256, 0, stream>>>(
+                      n, d_state.ptr, d_par_old.ptr, d_par.ptr);
+                    launched();
+                }
+                launched();
+                // One small record per trial step: [1] = state before the
+                // decision (+ the decision), [0] = state after it
+                GADFIT_CUDA_TRY(cudaMemcpyAsync(h_mirror,
+                                                d_state.ptr,
+                                                2 * sizeof(LmState),
+                                                cudaMemcpyDeviceToHost,
+                                                stream));
+                GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+                const LmState& now { h_mirror[0] };
+                const LmState& rec { h_mirror[1] };
+                trace.push_back(
+                  { rec.lambda, rec.new_chi2, rec.old_chi2, i_iteration, rec.decision });
+                lambda = now.lambda;
+                if (rec.decision == 0) {
+                    break;
+                }
+                if (rec.decision == 1) {
+                    lambda_lhs = lambda;
+                    solve_phase(false);
+                } else {
+                    --i_iteration;
+                    finished = true;
+                }
+            }
+            if (i_iteration == settings.iteration_limit) {
+                finished = true;
+            }
+        }
+        t_main.stop(stream);
+        n_iterations = i_iteration;
+        download_parameters();
+        for (PhaseTimer* t :
+             { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
+            t->collect();
+        }
+        fitted = true;
+    }
+
+    auto public_chi2() -> double
+    {
+        if (sets.empty()) {
+            return 0.0;
+        }
+        ensure_device();
+        upload_parameters();
+        chi2_phase(d_scratch.ptr);
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(
+          h_scalar, d_scratch.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        return h_scalar[0];
+    }
+
+    auto public_value(const double arg, const int i_dataset) -> double
+    {
+        if (i_dataset < 0 || i_dataset >= static_cast<int>(sets.size())) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "invalid data set index" };
+        }
+        ensure_device();
+        d_stage.ensure(std::max<size_t>(d_stage.capacity, NP));
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(d_stage.ptr,
+                                        par.data() + static_cast<size_t>(i_dataset) * NP,
+                                        NP * sizeof(double),
+                                        cudaMemcpyHostToDevice,
+                                        stream));
+        ops->value(stream, d_stage.ptr, arg, d_scratch.ptr);
+        launched();
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(
+          h_scalar, d_scratch.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        return h_scalar[0];
+    }
+
+    // -------------------------------------------------------------- getters
+
+    template <class T>
+    auto download(const T* src, const size_t n) -> std::vector<T>
+    {
+        std::vector<T> out(n);
+        if (n > 0) {
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(
+              out.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+        return out;
+    }
+
+    // Dense views of the block-arrow storage (single rank only)
+    auto dense_array(const int which) -> std::vector<double>
+    {
+        if (!fitted) {
+            throw StatusError { GADFIT_B200_NOT_AVAILABLE, "fit() has not been called" };
+        }
+        if (world > 1) {
+            throw StatusError { GADFIT_B200_NOT_AVAILABLE,
+                                "dense arrays are only assembled on a single rank" };
+        }
+        const int S { static_cast<int>(sets.size()) };
+        const size_t n { static_cast<size_t>(n_active) };
+        const int NA { NP + 1 };
+        const int NT { NA * (NA + 1) / 2 };
+        const auto need_dense { [&](const size_t rows) {
+            if (rows * n > kDenseLimit) {
+                throw StatusError { GADFIT_B200_NOT_AVAILABLE,
+                                    "dense array exceeds 2^27 entries" };
+            }
+        } };
+        GADFIT_CUDA_TRY(cudaSetDevice(device));
+        switch (which) {
+        case GADFIT_B200_JTJ:
+        case GADFIT_B200_LEFT_SIDE:
+        case GADFIT_B200_DTD:
+        case GADFIT_B200_INV_JTJ: {
+            need_dense(n);
+            std::vector<double> out(n * n, 0.0);
+            if (settings.iteration_limit == 0 && which != GADFIT_B200_DTD) {
+                return out; // fit() never computed a Jacobian
+            }
+            const bool want_jtj { which != GADFIT_B200_DTD };
+            std::vector<double> M;
+            std::vector<double> sums;
+            if (want_jtj) {
+                M = download(d_M.ptr, static_cast<size_t>(S) * NT);
+                sums = download(d_shared_sums.ptr,
+                                static_cast<size_t>(std::max(shared_len(), 1)));
+            }
+            const auto dl { download(d_dtd_local.ptr, static_cast<size_t>(S) * NP) };
+            const auto dg { download(d_dtd_global.ptr, static_cast<size_t>(std::max(pg, 1))) };
+            const double lam { which == GADFIT_B200_LEFT_SIDE ? lambda_lhs : 0.0 };
+            if (want_jtj) {
+                for (int a = 0; a < pg; ++a) {
+                    for (int b = a; b < pg; ++b) {
+                        const double v { sums[tri_index(pg, a, b)] };
+                        out[a * n + b] = v;
+                        out[b * n + a] = v;
+                    }
+                }
+                for (int s = 0; s < S; ++s) {
+                    const double* Ms { M.data() + static_cast<size_t>(s) * NT };
+                    for (int k = 0; k < NP; ++k) {
+                        const long long ck { column(s, k) };
+                        if (ck < pg) {
+                            continue; // passive or shared-shared (already done)
+                        }
+                        for (int m = 0; m < NP; ++m) {
+                            const long long cm { column(s, m) };
+                            if (cm < 0) {
+                                continue;
+                            }
+                            const double v { k <= m ? Ms[tri_index(NA, k, m)]
+                                                    : Ms[tri_index(NA, m, k)] };
+                            out[ck * n + cm] = v;
+                            out[cm * n + ck] = v;
+                        }
+                    }
+                }
+            }
+            if (which == GADFIT_B200_DTD || which == GADFIT_B200_LEFT_SIDE) {
+                const double f { which == GADFIT_B200_DTD ? 1.0 : lam };
+                for (int a = 0; a < pg; ++a) {
+                    out[a * n + a] += f * dg[a];
+                }
+                for (int s = 0; s < S; ++s) {
+                    for (int k = 0; k < NP; ++k) {
+                        const long long c { column(s, k) };
+                        if (c >= pg) {
+                            out[c * n + c] += f * dl[static_cast<size_t>(s) * NP + k];
+                        }
+                    }
+                }
+            }
+            if (which == GADFIT_B200_INV_JTJ) {
+                if (n > 128) {
+                    throw StatusError { GADFIT_B200_NOT_AVAILABLE,
+                                        "dense inverse limited to n <= 128" };
+                }
+                DeviceBuffer<double> dA, dL, dI;
+                dA.upload(out, stream);
+                dL.zero(n * n, stream);
+                dI.zero(n * n, stream);
+                k_dense_inverse<<<1, 1, 0, stream>>>(static_cast<int>(n), dA.ptr, dL.ptr, dI.ptr);
+                launched();
+                out = download(dI.ptr, n * n);
+            }
+            return out;
+        }
+        case GADFIT_B200_RIGHT_SIDE: {
+            std::vector<double> out(n, 0.0);
+            if (settings.iteration_limit == 0) {
+                return out;
+            }
+            const auto M { download(d_M.ptr, static_cast<size_t>(S) * NT) };
+            const auto sums { download(d_shared_sums.ptr, static_cast<size_t>(std::max(shared_len(), 1))) };
+            for (int a = 0; a < pg; ++a) {
+                out[a] = sums[pg * (pg + 1) / 2 + a];
+            }
+            for (int s = 0; s < S; ++s) {
+                for (int k = 0; k < NP; ++k) {
+                    const long long c { column(s, k) };
+                    if (c >= pg) {
+                        out[c] = M[static_cast<size_t>(s) * NT + tri_index(NA, k, NP)];
+                    }
+                }
+            }
+            return out;
+        }
+        case GADFIT_B200_DELTA1:
+        case GADFIT_B200_DELTA2: {
+            std::vector<double> out(n, 0.0);
+            if (settings.iteration_limit == 0
+                || (which == GADFIT_B200_DELTA2 && !have_delta2)) {
+                return out;
+            }
+            const auto d { download(which == GADFIT_B200_DELTA1 ? d_delta1_par.ptr
+                                                                 : d_delta2_par.ptr,
+                                    static_cast<size_t>(S) * NP) };
+            for (int s = 0; s < S; ++s) {
+                for (int k = 0; k < NP; ++k) {
+                    const long long c { column(s, k) };
+                    if (c >= 0) {
+                        out[c] = d[static_cast<size_t>(s) * NP + k];
+                    }
+                }
+            }
+            return out;
+        }
+        case GADFIT_B200_JACOBIAN:
+        case GADFIT_B200_RESIDUALS: {
+            const size_t N { static_cast<size_t>(n_datapoints) };
+            if (which == GADFIT_B200_JACOBIAN) {
+                need_dense(N);
+            }
+            std::vector<double> out(which == GADFIT_B200_JACOBIAN ? N * n : N, 0.0);
+            if (settings.iteration_limit == 0) {
+                return out;
+            }
+            // Re-run the Jacobian sweep at the parameters of the last
+            // Jacobian evaluation with row / residual output switched on
+            DeviceBuffer<double> keep;
+            const size_t n_par { static_cast<size_t>(S) * NP };
+            keep.ensure(n_par);
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(keep.ptr, d_par.ptr, n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, stream));
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr, d_par_jac.ptr, n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, stream));
+            d_J.ensure(static_cast<size_t>(NP) * N);
+            d_resid.ensure(N);
+            DeviceBuffer<double> scratch;
+            scratch.ensure(static_cast<size_t>(std::max(slots_jac.n_slots, 1)) * NT);
+            ops->jacobian(slots_jac.grid, stream, sweep_args(), settings.loss,
+                          slots_jac.base.ptr, scratch.ptr, d_J.ptr, d_resid.ptr,
+                          n_local_points);
+            launched();
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr, keep.ptr, n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, stream));
+            if (which == GADFIT_B200_RESIDUALS) {
+                return download(d_resid.ptr, N);
+            }
+            const auto J { download(d_J.ptr, static_cast<size_t>(NP) * N) };
+            size_t row { 0 };
+            for (int s = 0; s < S; ++s) {
+                for (int p = 0; p < sets[s].n; ++p, ++row) {
+                    for (int k = 0; k < NP; ++k) {
+                        const long long c { column(s, k) };
+                        if (c >= 0) {
+                            out[row * n + c] = J[static_cast<size_t>(k) * N + row];
+                        }
+                    }
+                }
+            }
+            return out;
+        }
+        default:
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "unknown array" };
+        }
+    }
+};
+
+} // namespace gadfit_b200
+
+struct gadfit_b200_solver : gadfit_b200::SolverImpl
+{};
+
+// ------------------------------------------------------------------- C-ABI
+//
+// Defined inside the namespace for name lookup only: functions with C
+// language linkage are the same functions as the ones the header declares.
+
+namespace gadfit_b200 {
+
+namespace {
+
+template <class F>
+auto guarded(gadfit_b200_solver* h, F&& f) -> int
+{
+    if (h == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    try {
+        f();
+        return GADFIT_B200_OK;
+    } catch (const StatusError& e) {
+        h->last_error = e.what();
+        return e.status;
+    } catch (const std::exception& e) {
+        h->last_error = e.what();
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+}
+
+struct ModelInfo
+{
+    const char* name;
+    int n_pars;
+};
+
+auto model_table() -> const std::vector<ModelInfo>&
+{
+    static const std::vector<ModelInfo> table { [] {
+        std::vector<ModelInfo> t;
+        models::for_each_model(
+          [&]<class Model>() { t.push_back({ Model::name, Model::n_pars }); });
+        return t;
+    }() };
+    return table;
+}
+
+} // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int gadfit_b200_n_models(void)
+{
+    return static_cast<int>(model_table().size());
+}
+
+int gadfit_b200_model_info(int i_model, const char** name, int* n_pars)
+{
+    if (i_model < 0 || i_model >= gadfit_b200_n_models()) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    *name = model_table()[i_model].name;
+    *n_pars = model_table()[i_model].n_pars;
+    return GADFIT_B200_OK;
+}
+
+int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out)
+{
+    if (model_name == nullptr || out == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    try {
+        auto ops { make_model_ops(model_name) };
+        if (!ops) {
+            return GADFIT_B200_UNKNOWN_MODEL;
+        }
+        auto* h { new gadfit_b200_solver {} };
+        h->NP = ops->n_pars();
+        h->ops = std::move(ops);
+        gadfit_b200_default_settings(&h->settings);
+        int dev { 0 };
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            h->device = dev;
+        } else {
+            (void)cudaGetLastError();
+        }
+        *out = h;
+        return GADFIT_B200_OK;
+    } catch (const std::exception&) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+}
+
+int gadfit_b200_destroy(gadfit_b200_solver* solver)
+{
+    delete solver;
+    return GADFIT_B200_OK;
+}
+
+int gadfit_b200_add_dataset(gadfit_b200_solver* solver,
+                            int n_datapoints,
+                            const double* x_data,
+                            const double* y_data,
+                            const double* errors_or_null)
+{
+    return guarded(solver, [&] {
+        solver->add_dataset(n_datapoints, x_data, y_data, errors_or_null);
+    });
+}
+
+int gadfit_b200_set_par(gadfit_b200_solver* solver,
+                        int i_par,
+                        double val,
+                        int active,
+                        int i_dataset,
+                        const char* name_or_null)
+{
+    return guarded(solver, [&] {
+        solver->set_par(i_par, val, active != 0, i_dataset);
+        // lm_solver.cpp:99-104
+        if (i_par >= static_cast<int>(solver->names.size())) {
+            solver->names.resize(i_par + 1);
+        }
+        if (name_or_null != nullptr && name_or_null[0] != '\0') {
+            solver->names[i_par] = name_or_null;
+        }
+    });
+}
+
+int gadfit_b200_default_settings(gadfit_b200_settings* out)
+{
+    if (out == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    // lm_solver.h:88-96
+    *out = { 1000, 3, 10.0, 10.0, 1, nullptr, 0, -1.0, 0U, GADFIT_B200_LOSS_LINEAR, 1 };
+    return GADFIT_B200_OK;
+}
+
+int gadfit_b200_set_settings(gadfit_b200_solver* solver, const gadfit_b200_settings* s)
+{
+    return guarded(solver, [&] {
+        if (s == nullptr) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "null settings" };
+        }
+        solver->settings = *s;
+        if (s->DTD_min != nullptr && s->n_DTD_min > 0) {
+            solver->DTD_min.assign(s->DTD_min, s->DTD_min + s->n_DTD_min);
+        } else {
+            solver->DTD_min = { 0.0 };
+        }
+        solver->settings.DTD_min = nullptr;
+    });
+}
+
+int gadfit_b200_fit(gadfit_b200_solver* solver, double lambda)
+{
+    return guarded(solver, [&] { solver->fit(lambda); });
+}
+
+int gadfit_b200_get_par(gadfit_b200_solver* solver, int i_par, int i_dataset, double* out)
+{
+    return guarded(solver, [&] {
+        if (i_par < 0 || i_par >= solver->NP || i_dataset < 0
+            || i_dataset >= static_cast<int>(solver->sets.size())) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "index out of range" };
+        }
+        *out = solver->par[static_cast<size_t>(i_dataset) * solver->NP + i_par];
+    });
+}
+
+int gadfit_b200_get_value(gadfit_b200_solver* solver, double arg, int i_dataset, double* out)
+{
+    return guarded(solver, [&] { *out = solver->public_value(arg, i_dataset); });
+}
+
+int gadfit_b200_chi2(gadfit_b200_solver* solver, double* out)
+{
+    return guarded(solver, [&] { *out = solver->public_chi2(); });
+}
+
+int gadfit_b200_dof(gadfit_b200_solver* solver, int* out)
+{
+    return guarded(solver, [&] { *out = solver->dof; });
+}
+
+int gadfit_b200_get_array(gadfit_b200_solver* solver,
+                          int which,
+                          double* buf,
+                          size_t cap,
+                          size_t* need)
+{
+    return guarded(solver, [&] {
+        const auto data { solver->dense_array(which) };
+        if (need != nullptr) {
+            *need = data.size();
+        }
+        const size_t n { std::min(cap, data.size()) };
+        if (buf != nullptr && n > 0) {
+            std::memcpy(buf, data.data(), n * sizeof(double));
+        }
+    });
+}
+
+int gadfit_b200_get_trace(gadfit_b200_solver* solver,
+                          gadfit_b200_trial* buf,
+                          size_t cap,
+                          size_t* n)
+{
+    return guarded(solver, [&] {
+        if (n != nullptr) {
+            *n = solver->trace.size();
+        }
+        const size_t m { std::min(cap, solver->trace.size()) };
+        if (buf != nullptr && m > 0) {
+            std::memcpy(buf, solver->trace.data(), m * sizeof(gadfit_b200_trial));
+        }
+    });
+}
+
+int gadfit_b200_n_iterations(gadfit_b200_solver* solver, int* out)
+{
+    return guarded(solver, [&] { *out = solver->n_iterations; });
+}
+
+int gadfit_b200_get_timings(gadfit_b200_solver* solver, gadfit_b200_timings* out)
+{
+    return guarded(solver, [&] {
+        const PhaseTimer* timers[5] { &solver->t_jacobian,
+                                      &solver->t_chi2,
+                                      &solver->t_linalg,
+                                      &solver->t_omega,
+                                      &solver->t_main };
+        for (int i = 0; i < 5; ++i) {
+            out->seconds[i] = timers[i]->seconds;
+            out->calls[i] = timers[i]->calls;
+        }
+    });
+}
+
+int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out)
+{
+    return guarded(solver, [&] { *out = solver->n_launches; });
+}
+
+int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
+                                     double* seconds_per_launch,
+                                     int* launches)
+{
+    return guarded(solver, [&] {
+        const auto& t { solver->t_jac_kernel };
+        *launches = t.calls;
+        *seconds_per_launch = t.calls > 0 ? t.seconds / t.calls : 0.0;
+    });
+}
+
+const char* gadfit_b200_last_error(gadfit_b200_solver* solver)
+{
+    return solver != nullptr ? solver->last_error.c_str() : "null solver";
+}
+
+const char* gadfit_b200_status_name(int status)
+{
+    static const char* names[] { "OK",
+                                 "UnknownOperation",
+                                 "LateAddDatasetCall",
+                                 "SetParInvalidIndex",
+                                 "UninitializedParameter",
+                                 "NegativeDegreesOfFreedom",
+                                 "NoFittingParameters",
+                                 "NoGlobalParameters",
+                                 "InsufficientIntegrationWorkspace",
+                                 "UnknownModel",
+                                 "CudaError",
+                                 "NcclError",
+                                 "InvalidArgument",
+                                 "NotAvailable" };
+    if (status < 0 || status > GADFIT_B200_NOT_AVAILABLE) {
+        return "?";
+    }
+    return names[status];
+}
+
+int gadfit_b200_set_device(gadfit_b200_solver* solver, int device)
+{
+    return guarded(solver, [&] {
+        if (solver->device_ready && device != solver->device) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT,
+                                "the device cannot change after first use" };
+        }
+        solver->device = device;
+    });
+}
+
+int gadfit_b200_upload(gadfit_b200_solver* solver)
+{
+    return guarded(solver, [&] {
+        if (!solver->data_uploaded) {
+            solver->upload_data();
+        }
+    });
+}
+
+int gadfit_b200_comm_unique_id(void* id_128_bytes)
+{
+    try {
+        auto& nccl { Nccl::instance() };
+        ncclUniqueId id {};
+        static_assert(sizeof(ncclUniqueId) == 128);
+        nccl.check(nccl.getUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(id_128_bytes, &id, sizeof(id));
+        return GADFIT_B200_OK;
+    } catch (const std::exception&) {
+        return GADFIT_B200_NCCL_ERROR;
+    }
+}
+
+int gadfit_b200_set_comm(gadfit_b200_solver* solver,
+                         int rank,
+                         int world_size,
+                         const void* id_128_bytes)
+{
+    return guarded(solver, [&] {
+        if (world_size < 1 || rank < 0 || rank >= world_size) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "bad rank / world size" };
+        }
+        solver->ensure_device();
+        if (world_size > 1) {
+            auto& nccl { Nccl::instance() };
+            ncclUniqueId id {};
+            std::memcpy(&id, id_128_bytes, sizeof(id));
+            nccl.check(nccl.commInitRank(&solver->comm, world_size, id, rank),
+                       "ncclCommInitRank");
+        }
+        solver->rank = rank;
+        solver->world = world_size;
+        solver->data_uploaded = false;
+    });
+}
+
+int gadfit_b200_partition(int n_datasets,
+                          const int* n_points,
+                          int rank,
+                          int world_size,
+                          int* first_dataset,
+                          int* end_dataset,
+                          int* split)
+{
+    if (n_datasets < 0 || n_points == nullptr || world_size < 1 || rank < 0
+        || rank >= world_size) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    const Partition part { compute_partition(n_datasets, n_points, rank, world_size) };
+    *first_dataset = part.first;
+    *end_dataset = part.end;
+    *split = part.split ? 1 : 0;
+    return GADFIT_B200_OK;
+}
+
+} // extern "C"
+#pragma GCC visibility pop
+
+} // namespace gadfit_b200

@@ -19,6 +19,12 @@
 
 #include <stddef.h>
 
+#if defined(__GNUC__)
+#define GADFIT_B200_API __attribute__((visibility("default")))
+#else
+#define GADFIT_B200_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -112,19 +118,19 @@ typedef struct gadfit_b200_timings
  * selected by name from the functions compiled into the library
  * (include/gadfit_b200/fit_models.h); a std::function cannot run on the
  * device. */
-int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out);
-int gadfit_b200_destroy(gadfit_b200_solver* solver);
+GADFIT_B200_API int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out);
+GADFIT_B200_API int gadfit_b200_destroy(gadfit_b200_solver* solver);
 
 /* Number of registered fitting functions / name and parameter count of one */
-int gadfit_b200_n_models(void);
-int gadfit_b200_model_info(int i_model, const char** name, int* n_pars);
+GADFIT_B200_API int gadfit_b200_n_models(void);
+GADFIT_B200_API int gadfit_b200_model_info(int i_model, const char** name, int* n_pars);
 
 /* LMsolver::addDataset(n, x, y, errors = nullptr), lm_solver.h:164-167,
  * lm_solver.cpp:30-56.  Arrays are BORROWED until fit() has uploaded them
  * (first fit() or gadfit_b200_upload()).  With a communicator attached, x/y
  * may be NULL on ranks that do not own the dataset (see
  * gadfit_b200_owned_datasets). */
-int gadfit_b200_add_dataset(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_add_dataset(gadfit_b200_solver* solver,
                             int n_datapoints,
                             const double* x_data,
                             const double* y_data,
@@ -132,7 +138,7 @@ int gadfit_b200_add_dataset(gadfit_b200_solver* solver,
 
 /* LMsolver::setPar(i_par, val, active, i_dataset = -1, name = ""),
  * lm_solver.h:171-180, lm_solver.cpp:58-113.  i_dataset = -1: global. */
-int gadfit_b200_set_par(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_set_par(gadfit_b200_solver* solver,
                         int i_par,
                         double val,
                         int active,
@@ -140,63 +146,63 @@ int gadfit_b200_set_par(gadfit_b200_solver* solver,
                         const char* name_or_null);
 
 /* LMsolver::settings, lm_solver.h:198-210 */
-int gadfit_b200_default_settings(gadfit_b200_settings* out);
-int gadfit_b200_set_settings(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_default_settings(gadfit_b200_settings* out);
+GADFIT_B200_API int gadfit_b200_set_settings(gadfit_b200_solver* solver,
                              const gadfit_b200_settings* settings);
 
 /* LMsolver::fit(lambda = 10), lm_solver.h:181, lm_solver.cpp:401-511 */
-int gadfit_b200_fit(gadfit_b200_solver* solver, double lambda);
+GADFIT_B200_API int gadfit_b200_fit(gadfit_b200_solver* solver, double lambda);
 
 /* getParValue / getValue / chi2 / degreesOfFreedom,
  * lm_solver.h:182-187,195, lm_solver.cpp:513-534,688-696 */
-int gadfit_b200_get_par(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_get_par(gadfit_b200_solver* solver,
                         int i_par,
                         int i_dataset,
                         double* out);
-int gadfit_b200_get_value(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_get_value(gadfit_b200_solver* solver,
                           double arg,
                           int i_dataset,
                           double* out);
-int gadfit_b200_chi2(gadfit_b200_solver* solver, double* out);
-int gadfit_b200_dof(gadfit_b200_solver* solver, int* out);
+GADFIT_B200_API int gadfit_b200_chi2(gadfit_b200_solver* solver, double* out);
+GADFIT_B200_API int gadfit_b200_dof(gadfit_b200_solver* solver, int* out);
 
 /* getJacobian/getJTJ/getDTD/getLeftSide/getRightSide/getResiduals/getInvJTJ,
  * lm_solver.h:188-194, lm_solver.cpp:536-585.  Writes min(cap, need) doubles;
  * *need is the full length.  Dense n x n / N x n outputs are materialised on
  * demand from the block-arrow storage and refused with
  * GADFIT_B200_NOT_AVAILABLE beyond 2^27 entries. */
-int gadfit_b200_get_array(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_get_array(gadfit_b200_solver* solver,
                           int which,
                           double* buf,
                           size_t cap,
                           size_t* need);
 
 /* Accept/reject history of the last fit() (see gadfit_b200_trial) */
-int gadfit_b200_get_trace(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_get_trace(gadfit_b200_solver* solver,
                           gadfit_b200_trial* buf,
                           size_t cap,
                           size_t* n);
 /* Number of successful iterations of the last fit(), lm_solver.cpp:439-501 */
-int gadfit_b200_n_iterations(gadfit_b200_solver* solver, int* out);
-int gadfit_b200_get_timings(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_n_iterations(gadfit_b200_solver* solver, int* out);
+GADFIT_B200_API int gadfit_b200_get_timings(gadfit_b200_solver* solver,
                             gadfit_b200_timings* out);
 /* Kernels launched by this solver since creation */
-int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out);
+GADFIT_B200_API int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out);
 /* Average device time [s] of the Jacobian-sweep kernel alone in the last
  * fit() (CUDA events on the solver's stream) and the number of launches */
-int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
                                      double* seconds_per_launch,
                                      int* launches);
 
-const char* gadfit_b200_last_error(gadfit_b200_solver* solver);
-const char* gadfit_b200_status_name(int status);
+GADFIT_B200_API const char* gadfit_b200_last_error(gadfit_b200_solver* solver);
+GADFIT_B200_API const char* gadfit_b200_status_name(int status);
 
 /* ---- device / multi-GPU plumbing (no reference counterpart) ------------- */
 
 /* CUDA device of this solver (default: the current device at create) */
-int gadfit_b200_set_device(gadfit_b200_solver* solver, int device);
+GADFIT_B200_API int gadfit_b200_set_device(gadfit_b200_solver* solver, int device);
 /* Copy the borrowed data sets to HBM now instead of at the first fit() */
-int gadfit_b200_upload(gadfit_b200_solver* solver);
+GADFIT_B200_API int gadfit_b200_upload(gadfit_b200_solver* solver);
 
 /* One process per GPU.  Rank 0 obtains an id, the caller broadcasts the 128
  * bytes (torch.distributed / MPI / sockets) and every rank attaches.  All
@@ -206,8 +212,8 @@ int gadfit_b200_upload(gadfit_b200_solver* solver);
  * data sets (or the slice of points) it owns, and only the shared-parameter
  * normal block, its right-hand side and chi2 are all-reduced per trial step
  * (the reference's co_sum of the dense JTJ, gadfit.F90:700-701,735,1032). */
-int gadfit_b200_comm_unique_id(void* id_128_bytes);
-int gadfit_b200_set_comm(gadfit_b200_solver* solver,
+GADFIT_B200_API int gadfit_b200_comm_unique_id(void* id_128_bytes);
+GADFIT_B200_API int gadfit_b200_set_comm(gadfit_b200_solver* solver,
                          int rank,
                          int world_size,
                          const void* id_128_bytes);
@@ -215,7 +221,7 @@ int gadfit_b200_set_comm(gadfit_b200_solver* solver,
  * first/last+1 owned data set, or -- when there are fewer data sets than
  * ranks -- every data set with the point slice [*point_begin, *point_end)
  * expressed as fractions k/world of each data set (then *split = 1). */
-int gadfit_b200_partition(int n_datasets,
+GADFIT_B200_API int gadfit_b200_partition(int n_datasets,
                           const int* n_points,
                           int rank,
                           int world_size,
@@ -225,7 +231,10 @@ int gadfit_b200_partition(int n_datasets,
 
 /* FP64 FMA peak of the current device measured by a register-resident DFMA
  * loop on every SM [FLOP/s]; the roofline denominator of bench.py */
-int gadfit_b200_measure_fp64_peak(double* flops_per_second);
+GADFIT_B200_API int gadfit_b200_measure_fp64_peak(double* flops_per_second);
+/* Diagnostics behind DESIGN.md's kernel choices: which = 0 DFMA vector pipe,
+ * 1 DMMA (mma.sync.m8n8k4.f64), 2 both interleaved in one warp [FLOP/s] */
+GADFIT_B200_API int gadfit_b200_microbench(int which, double* flops_per_second);
 
 #ifdef __cplusplus
 }

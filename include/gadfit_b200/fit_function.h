@@ -47,6 +47,7 @@ struct QuadratureMixin
 struct ValueCtx : QuadratureMixin
 {
     const double* p;
+    GADFIT_HD explicit ValueCtx(const double* p) : p { p } {}
     template <int K>
     GADFIT_HD Passive get() const
     {
@@ -57,6 +58,7 @@ struct ValueCtx : QuadratureMixin
 struct GradCtx : QuadratureMixin
 {
     const double* p;
+    GADFIT_HD explicit GradCtx(const double* p) : p { p } {}
     template <int K>
     GADFIT_HD SDual<(1U << K)> get() const
     {
@@ -72,6 +74,8 @@ struct Dir2Ctx : QuadratureMixin
     const double* p;
     // Direction: delta1 of the column this parameter maps to, 0 if passive
     const double* seed;
+    GADFIT_HD Dir2Ctx(const double* p, const double* seed) : p { p }, seed { seed }
+    {}
     template <int K>
     GADFIT_HD Dir2 get() const
     {
