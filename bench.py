@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the LM inner loop (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference          # the reference's CPU path
+
+A *step* is one LM iteration of the global fit: Jacobian sweep over every
+point of every data set + block-arrow solve + chi2 sweep(s) of the trial
+step(s).  The workload at N = 1 is BASELINE config 2 at full size (64 data
+sets x 1M points, 20 shared parameters, FP64); at N > 1 every rank owns 64
+such data sets (weak scaling) and only the 20 x 20 shared normal block, its
+right-hand side and chi2 are all-reduced (NCCL) per trial step.
+
+value   Jacobian entries (structural non-zeros, all ranks) processed per second
+        of the timed K iterations, data resident in HBM.
+e2e     the same through the public API from pinned HOST buffers: create,
+        addDataset x S, setPar, fit(K iterations) incl. the H2D upload, and the
+        read-back of chi2 + parameters.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SETS_PER_GPU = {"C2": 64, "C3": 1000, "C4": 256, "C5": 100_000}
+POINTS = {"C2": 1_000_000, "C3": 4096, "C4": 65536, "C5": 256}
+DESCRIPTION = {
+    "C2": "BASELINE config 2: 64 data sets x 1M points per GPU, 3 distorted Gaussians, 20 shared parameters",
+    "C3": "BASELINE config 3: 1000 x 4096 per GPU, Gaussian + linear background, 4 local + 2 shared",
+    "C4": "BASELINE config 4: 256 x 65536 per GPU, single-integral model + geodesic acceleration",
+    "C5": "BASELINE config 5: 100000 x 256 per GPU, Lorentzian + double-integral term, 3 local + 4 shared",
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C2", choices=list(SETS_PER_GPU))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sets", type=int, default=0, help="data sets per GPU (default: full size)")
+    ap.add_argument("--points", type=int, default=0, help="points per data set (default: full size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------- clock sampler
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------ reference (CPU)
+
+def reference_api():
+    """The reference's own CPU implementation, compiled from its unmodified
+    sources (oracle/_ref, kind 'reference'); else the oracle's CPU restatement
+    (kind 'port').  Used only as the timed CPU baseline."""
+    from gadfit_b200._capi import Api
+    fast = os.path.join(ROOT, "oracle", "_ref", "libgadfit_ref_fast.so")
+    if os.path.exists(fast):
+        return Api(fast, "gadfit_ref_", product=False), "reference"
+    port = os.path.join(ROOT, "oracle", "_build", "libgadfit_oracle.so")
+    return Api(port, "gadfit_oracle_", product=False), "port"
+
+
+def run_cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 20.0) -> dict:
+    """Times the CPU reference on a bounded sample of the same workload: same
+    model, parameters, settings; fewer data sets / points so that the run ends
+    within ~budget_s seconds.  Reports Jacobian entries/s over whole LM
+    iterations (same definition as the GPU value)."""
+    from gadfit_b200 import workloads as W
+    from gadfit_b200.lm_solver import LMsolver
+
+    api, kind = reference_api()
+    cores = os.cpu_count() or 1
+    full_sets, full_points = SETS_PER_GPU[workload], POINTS[workload]
+    # the dense reference is limited by n = p_g + S p_l
+    sets = {"C2": 8, "C3": 16, "C4": 16, "C5": 32}[workload]
+    points = min(full_points, {"C2": 125_000, "C3": 4096, "C4": 2048, "C5": 256}[workload])
+    iters = max(1, min(steps, 3))
+
+    def once(n_sets, n_points, n_iter):
+        w = W.WORKLOADS[workload](n_sets=n_sets, n_points=n_points, iteration_limit=n_iter)
+        s = LMsolver(w.model, _api=api)
+        w.setup(s)
+        s.settings.n_threads = cores
+        t0 = time.perf_counter()
+        s.fit(w.lambda0)
+        dt = time.perf_counter() - t0
+        tm = s.timings()
+        done = max(s.iterations(), 1)
+        return w, dt, tm, done
+
+    # calibration on a small instance, then scale the points to the budget
+    w, dt, tm, done = once(sets, max(points // 8, 64), 1)
+    per_point_iter = dt / (w.n_total * done)
+    target = int(budget_s / (per_point_iter * iters * sets))
+    points = int(max(64, min(points, target)))
+    w, dt, tm, done = once(sets, points, iters)
+    value = w.nnz_jacobian * done / tm["main"][0] if tm["main"][0] > 0 else w.nnz_jacobian * done / dt
+    jac_sweep = tm["jacobian"][0] / max(tm["jacobian"][1], 1)
+    return {
+        "value": value, "unit": "jacobian_entries/s", "cores": cores, "kind": kind,
+        "sample": f"{workload} model/settings, {sets} data sets x {points} points, {done} LM iterations, "
+                  f"all {cores} host threads (OpenMP), in-tree linear algebra",
+        "lm_iterations_per_s": done / dt,
+        "jacobian_sweep_entries_per_s": w.nnz_jacobian / jac_sweep if jac_sweep > 0 else None,
+        "seconds": dt,
+    }
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    base = run_cpu_baseline(args.workload, args.steps, args.warmup, budget_s=30.0)
+    line = {
+        "impl": "reference",
+        "metric": "jacobian_entries_per_s", "value": base["value"], "unit": "jacobian_entries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / base["lm_iterations_per_s"] if base["lm_iterations_per_s"] else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": DESCRIPTION[args.workload] + " -- bounded sample: " + base["sample"]},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "jacobian_entries/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lm_iterations_per_s": base["lm_iterations_per_s"],
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from gadfit_b200 import LMsolver, comm_unique_id, measure_fp64_peak
+    from gadfit_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    uid = None
+    if world > 1:
+        buf = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    sets_per_gpu = args.sets or SETS_PER_GPU[args.workload]
+    n_points = args.points or POINTS[args.workload]
+    n_sets = sets_per_gpu * world
+    owned = range(rank * sets_per_gpu, (rank + 1) * sets_per_gpu)
+
+    # Pinned host buffers: rank-local data only (3 x 8 B per owned point)
+    pinned = []
+
+    def alloc(n):
+        t = torch.empty(n, dtype=torch.float64, pin_memory=(n * 8 <= (8 << 30)))
+        pinned.append(t)
+        return t.numpy()
+
+    w = W.WORKLOADS[args.workload](n_sets=n_sets, n_points=n_points, alloc=alloc, owned=owned,
+                                   iteration_limit=args.steps)
+
+    def new_solver(limit):
+        s = LMsolver(w.model)
+        s.setDevice(local_rank)
+        if world > 1:
+            s.setComm(rank, world, uid)
+        w.setup(s, owned=owned if world > 1 else None, pointers=False)
+        s.settings.iteration_limit = limit
+        return s
+
+    fp64_peak = measure_fp64_peak()
+
+    # ---- device-resident arm: upload once, warm up, then time K iterations
+    solver = new_solver(args.warmup)
+    solver.upload()
+    barrier()
+    if args.warmup > 0:
+        solver.fit(w.lambda0)                      # W untimed warm-up iterations
+    # reset to the start values: the timed fit does the same work as the
+    # reference would from the same initial guess
+    for k in w.shared:
+        solver.setPar(k, float(w.start[0, k]), True)
+    for s_ in (owned if world > 1 else range(n_sets)):
+        for k in w.local:
+            solver.setPar(k, float(w.start[s_, k]), True, s_)
+    solver.settings.iteration_limit = args.steps
+    launches0 = solver.launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    solver.fit(w.lambda0)
+    torch.cuda.synchronize()
+    t_local = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    seconds = max_over_ranks(t_local)
+    done = solver.iterations()
+    launches = solver.launches() - launches0
+    tm = solver.timings()
+    k1_sec, k1_calls = solver.jacobianKernelTime()
+    k1_sec = max_over_ranks(k1_sec)
+    device_main = max_over_ranks(tm["main"][0])
+    trials = len(solver.trace())
+    accepted = [t for t in solver.trace() if t["decision"] == 0]
+    chi2 = accepted[-1]["new_chi2"] if accepted else float("nan")
+
+    nnz_total = w.nnz_jacobian                       # all ranks
+    points_per_gpu = sets_per_gpu * n_points
+    value = nnz_total * done / seconds
+
+    # ---- roofline of the dominant kernel (Jacobian sweep), per launch
+    flops_per_launch = w.k1_flops_per_point() * points_per_gpu
+    bytes_per_launch = 24 * points_per_gpu
+    achieved_tflops = flops_per_launch / k1_sec / 1e12 if k1_sec > 0 else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "fp64", "kernel": "k_jacobian",
+        "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+        "frac": achieved_tflops / (fp64_peak / 1e12) if achieved_tflops else None,
+        "peak_source": "DFMA micro-benchmark measured live on this GPU (gadfit_b200_measure_fp64_peak); "
+                       "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
+        "flops_per_point": w.k1_flops_per_point(), "points_per_launch": points_per_gpu,
+        "seconds_per_launch": k1_sec, "launches_timed": k1_calls,
+        "hbm": {"achieved": bytes_per_launch / k1_sec / 1e9 if k1_sec > 0 else None,
+                "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_launch / k1_sec / 1e9 / hbm_peak if k1_sec > 0 else None,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650"},
+        "traffic": None,
+    }
+
+    # ---- end-to-end arm: public API from pinned host buffers, H2D inside
+    e2e = None
+    if not args.no_e2e:
+        del solver
+        barrier()
+        t0 = time.perf_counter()
+        s2 = new_solver(args.steps)
+        s2.fit(w.lambda0)
+        out = [s2.chi2()] + [s2.getParValue(k, owned[0]) for k in range(w.n_pars)]
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        barrier()
+        t_e2e = max_over_ranks(t_e2e)
+        done2 = max(s2.iterations(), 1)
+        e2e = {
+            "value": nnz_total * done2 / t_e2e, "unit": "jacobian_entries/s",
+            "h2d_bytes_per_step": int(24 * points_per_gpu / done2),
+            "d2h_bytes_per_step": int(8 * (sets_per_gpu * w.n_pars + 1) / done2) + 80 * max(len(s2.trace()), 1) // done2,
+            "seconds": t_e2e, "steps": done2,
+            "note": "one fit() of K iterations from pinned host buffers per GPU: the H2D copy of x, y, sigma "
+                    "(24 B/point) happens once per fit and is amortised over the K steps",
+            "lm_iterations_per_s": done2 / t_e2e,
+            "chi2": out[0],
+        }
+        del s2
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            b = run_cpu_baseline(args.workload, args.steps, args.warmup)
+            cpu_baseline = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu_baseline["lm_iterations_per_s"] = b["lm_iterations_per_s"]
+            cpu_baseline["jacobian_sweep_entries_per_s"] = b["jacobian_sweep_entries_per_s"]
+        except Exception as exc:  # the baseline must never take the GPU line down
+            cpu_baseline = {"value": None, "unit": "jacobian_entries/s", "cores": os.cpu_count(),
+                            "kind": "unavailable", "sample": repr(exc)}
+
+    if rank == 0:
+        line = {
+            "metric": "jacobian_entries_per_s", "value": value, "unit": "jacobian_entries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": seconds / max(done, 1) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": DESCRIPTION[args.workload],
+                "data_sets_per_gpu": sets_per_gpu, "points_per_data_set": n_points,
+                "parameters": {"shared": len(w.shared), "local_per_data_set": len(w.local)},
+                "settings": w.settings | {"lambda0": w.lambda0, "iteration_limit": args.steps},
+                "l2": "inputs (24 B/point x %d points = %.2f GB per GPU) are larger than the 126 MB L2"
+                      % (points_per_gpu, 24 * points_per_gpu / 1e9),
+                "parallelism": "one process per GPU; data sets sharded; NCCL all-reduce of the shared "
+                               "normal block + chi2 per trial step" if world > 1 else "single GPU",
+            },
+            "lm_iterations_per_s": done / seconds,
+            "iterations_done": done, "trial_steps": trials, "final_chi2": chi2,
+            "k1_sweep_entries_per_s": (nnz_total / world) / k1_sec * world if k1_sec > 0 else None,
+            "device_seconds_main_loop": device_main,
+            "phase_seconds": {k: v[0] for k, v in tm.items()},
+            "phase_calls": {k: v[1] for k, v in tm.items()},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "e2e": e2e,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

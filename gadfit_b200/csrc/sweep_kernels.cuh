@@ -153,23 +153,44 @@ struct JacobianShape
     static constexpr int NP { Model::n_pars };
     static constexpr int NA { NP + 1 };
     static constexpr int NT { NA * (NA + 1) / 2 };
-    // Odd leading dimension: conflict-free 64-bit stores of one row per thread
-    static constexpr int LD { (NA % 2 == 0) ? NA + 1 : NA };
-    // Triangle entries per thread / point groups per entry
-    static constexpr int EPT { (NT + kThreads - 1) / kThreads };
-    static constexpr int PG { NT >= kThreads ? 1 : kThreads / NT };
-    static constexpr size_t smem_bytes { sizeof(double)
-                                         * (static_cast<size_t>(kTile) * LD
-                                            + (PG > 1 ? static_cast<size_t>(PG) * NT : 0)) };
+    // The augmented row is cut into NB blocks of 8 columns (zero padded); the
+    // upper triangle of M has NBT blocks of 8 x 8
+    static constexpr int NB { (NA + 7) / 8 };
+    static constexpr int NBT { NB * (NB + 1) / 2 };
+    // Staging buffer, column major: A[column][point], leading dimension
+    // kTile + 4 so that the DMMA fragment loads are bank-conflict free
+    // ((row * LDP + point) mod 16 distinct over a half warp)
+    static constexpr int LDP { kTile + 4 };
+    static constexpr int kWarps { kThreads / 32 };
+    static constexpr size_t stage_doubles { static_cast<size_t>(NB) * 8 * LDP };
+    static constexpr size_t flush_doubles { static_cast<size_t>(kWarps) * NBT * 64 };
+    static constexpr size_t smem_bytes {
+        sizeof(double) * (stage_doubles > flush_doubles ? stage_doubles : flush_doubles)
+    };
 };
 
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor path (SASS: DMMA.884)
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
+{
+    asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
 // One thread per point evaluates f and its gradient (static-sparsity forward
-// mode), forms the augmented row and stages it in shared memory; the CTA then
-// accumulates the packed triangle of sum a a^T with every thread owning one
-// triangle entry (and one of PG point groups when the triangle is smaller
-// than the CTA).  If J_out != nullptr the weighted Jacobian rows are stored
-// parameter-major (J_out[k * n_points + i]) for the omega sweep and
-// getJacobian(); if r_out != nullptr so are the weighted residuals.
+// mode) and writes its augmented row, column major, into the staging buffer.
+// Each WARP then contracts its own 32 rows on the FP64 tensor path:
+// for every k-step of 4 points, lane l loads J[point l%4][column 8b + l/4] for
+// the NB column blocks -- the same register is the A fragment (J^T, 8 x 4) of
+// block row b and the B fragment (J, 4 x 8) of block column b -- and issues
+// one DMMA per upper-triangle block.  A warp only reads what it wrote itself,
+// so the steady state needs __syncwarp() only; the accumulators (2 doubles per
+// block and lane) stay in registers across all tiles of a data set and the 8
+// warps are summed in fixed order when the data set changes.
+// If J_out != nullptr the weighted Jacobian rows are stored parameter-major
+// (J_out[k * n_points + i]) for the omega sweep and getJacobian(); if
+// r_out != nullptr so are the weighted residuals.
 template <class Model>
 __global__ void __launch_bounds__(kThreads)
   k_jacobian(const SweepArgs a,
@@ -184,34 +205,31 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int NP { Shape::NP };
     constexpr int NA { Shape::NA };
     constexpr int NT { Shape::NT };
-    constexpr int LD { Shape::LD };
-    constexpr int EPT { Shape::EPT };
-    constexpr int PG { Shape::PG };
-    extern __shared__ double s_dyn[];
-    double* s_A { s_dyn };                 // [kTile][LD]
-    double* s_grp { s_dyn + kTile * LD };  // [PG][NT] (PG > 1 only)
+    constexpr int NB { Shape::NB };
+    constexpr int NBT { Shape::NBT };
+    constexpr int LDP { Shape::LDP };
+    constexpr int kWarps { Shape::kWarps };
+    extern __shared__ double s_A[]; // [NB * 8][LDP], reused by flush()
     __shared__ double s_par[NP];
 
     const int tid { static_cast<int>(threadIdx.x) };
-    // Triangle entries owned by this thread
-    int ei[EPT];
-    int ej[EPT];
-    double acc[EPT];
-    const int q { PG > 1 ? tid / NT : 0 }; // point group
-    const bool worker { PG > 1 ? (q < PG) : true };
+    const int lane { tid & 31 };
+    const int warp { tid >> 5 };
+    const int frag_row { lane >> 2 }; // column within a block of 8
+    const int frag_pt { lane & 3 };   // point within a k-step of 4
+
+    double acc[NBT][2];
 #pragma unroll
-    for (int m = 0; m < EPT; ++m) {
-        const int e { PG > 1 ? tid % NT : tid + m * kThreads };
-        int i { 0 };
-        int rem { e };
-        while (i < NA - 1 && rem >= NA - i) {
-            rem -= NA - i;
-            ++i;
-        }
-        ei[m] = (e < NT) ? i : 0;
-        ej[m] = (e < NT) ? i + rem : 0;
-        acc[m] = 0.0;
+    for (int b = 0; b < NBT; ++b) {
+        acc[b][0] = 0.0;
+        acc[b][1] = 0.0;
     }
+    const auto zero_padding { [&]() {
+        for (int idx = tid; idx < (NB * 8 - NA) * LDP; idx += kThreads) {
+            s_A[NA * LDP + idx] = 0.0;
+        }
+    } };
+    zero_padding();
 
     const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
                                     / gridDim.x) };
@@ -220,35 +238,37 @@ __global__ void __launch_bounds__(kThreads)
     int slot { slot_base[blockIdx.x] };
     int cur_set { -1 };
 
+    // Sum the warps in fixed order and write one partial (packed triangle)
     const auto flush { [&]() {
-        // Sum the point groups in fixed order, then write one partial
-        if constexpr (PG > 1) {
-            __syncthreads();
-            if (worker) {
-                s_grp[q * NT + tid % NT] = acc[0];
-            }
-            __syncthreads();
-            if (tid < NT) {
-                double total { 0.0 };
+        __syncthreads();
 #pragma unroll
-                for (int g = 0; g < PG; ++g) {
-                    total += s_grp[g * NT + tid];
-                }
-                partials[static_cast<long long>(slot) * NT + tid] = total;
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < EPT; ++m) {
-                const int e { tid + m * kThreads };
-                if (e < NT) {
-                    partials[static_cast<long long>(slot) * NT + e] = acc[m];
-                }
-            }
+        for (int b = 0; b < NBT; ++b) {
+            double* dst { s_A + (warp * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
+            dst[0] = acc[b][0];
+            dst[1] = acc[b][1];
+            acc[b][0] = 0.0;
+            acc[b][1] = 0.0;
         }
+        __syncthreads();
+        for (int e = tid; e < NT; e += kThreads) {
+            int i { 0 };
+            int rem { e };
+            while (rem >= NA - i) {
+                rem -= NA - i;
+                ++i;
+            }
+            const int j { i + rem };
+            const int blk { tri_index(NB, i >> 3, j >> 3) };
+            const int within { (i & 7) * 8 + (j & 7) };
+            double total { 0.0 };
 #pragma unroll
-        for (int m = 0; m < EPT; ++m) {
-            acc[m] = 0.0;
+            for (int w = 0; w < kWarps; ++w) {
+                total += s_A[(w * NBT + blk) * 64 + within];
+            }
+            partials[static_cast<long long>(slot) * NT + e] = total;
         }
+        __syncthreads();
+        zero_padding();
         ++slot;
     } };
 
@@ -262,47 +282,60 @@ __global__ void __launch_bounds__(kThreads)
             if (tid < NP) {
                 s_par[tid] = a.par[static_cast<long long>(s) * NP + tid];
             }
+            __syncthreads();
             cur_set = s;
         }
-        __syncthreads(); // s_par visible; previous tile's s_A fully consumed
         const int len { a.tile_len[t] };
+        if (warp * 32 >= len) {
+            continue; // nothing for this warp in a tail tile
+        }
+        double* column { s_A + tid };
         if (tid < len) {
             const long long i { a.tile_off[t] + tid };
-            const double inv_sig_den { a.sig[i] };
+            const double inv_sig { 1.0 / a.sig[i] };
             const auto f { Model {}(GradCtx { s_par }, a.x[i]) };
-            // lm_solver.cpp:303-310
-            const double res { (a.y[i] - f.val) / inv_sig_den };
+            // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
+            const double res { (a.y[i] - f.val) * inv_sig };
             const double w { loss_weight(loss_type, res) };
+            const double scale { w * inv_sig };
             double g[NP];
             dense_gradient<NP>(f, g);
-            double* row { s_A + tid * LD };
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                // lm_solver.cpp:315-317
-                const double jk { w * g[k] / inv_sig_den };
-                row[k] = jk;
+                const double jk { g[k] * scale };
+                column[k * LDP] = jk;
                 if (J_out != nullptr) {
                     J_out[static_cast<long long>(k) * n_points + i] = jk;
                 }
             }
-            row[NP] = w * res;
+            column[NP * LDP] = w * res;
             if (r_out != nullptr) {
                 r_out[i] = w * res;
             }
-        }
-        __syncthreads();
-        if (worker) {
+        } else {
 #pragma unroll
-            for (int m = 0; m < EPT; ++m) {
-                const int i { ei[m] };
-                const int j { ej[m] };
-                double sum { acc[m] };
-                for (int p = q; p < len; p += PG) {
-                    sum = ::fma(s_A[p * LD + i], s_A[p * LD + j], sum);
-                }
-                acc[m] = sum;
+            for (int k = 0; k < NA; ++k) {
+                column[k * LDP] = 0.0;
             }
         }
+        __syncwarp();
+        const double* frag_src { s_A + frag_row * LDP + warp * 32 + frag_pt };
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            double frag[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                frag[b] = frag_src[b * 8 * LDP + ks * 4];
+            }
+#pragma unroll
+            for (int bi = 0; bi < NB; ++bi) {
+#pragma unroll
+                for (int bj = bi; bj < NB; ++bj) {
+                    dmma_m8n8k4(acc[tri_index(NB, bi, bj)], frag[bi], frag[bj]);
+                }
+            }
+        }
+        __syncwarp();
     }
     if (cur_set >= 0) {
         flush();

@@ -100,6 +100,7 @@ class Workload:
     lambda0: float = 10.0
     settings: dict = field(default_factory=dict)
     f_val: int = 0          # algorithmic flops of one passive evaluation
+    first_set: int = 0      # x / y / sigma hold data sets [first_set, first_set + n_held)
 
     @property
     def n_total(self) -> int:
@@ -116,7 +117,8 @@ class Workload:
         return 4 * self.f_val + (2 + p) + 2 * (p * (p + 1) // 2 + p + 1)
 
     def slice(self, s: int):
-        a, b = s * self.n_points, (s + 1) * self.n_points
+        a = (s - self.first_set) * self.n_points
+        b = a + self.n_points
         return self.x[a:b], self.y[a:b], self.sigma[a:b]
 
     def setup(self, solver, owned: range | None = None, pointers: bool = False):
@@ -147,7 +149,8 @@ class Workload:
 def _make(name, model, n_sets, n_points, x_range, sigma, seed, truth, shared,
           local, settings, f_val, alloc=None, owned: range | None = None):
     n_pars = truth.shape[1]
-    total = n_sets * n_points
+    held = range(n_sets) if owned is None else owned
+    total = len(held) * n_points
     if alloc is None:
         x = np.empty(total)
         y = np.empty(total)
@@ -156,17 +159,16 @@ def _make(name, model, n_sets, n_points, x_range, sigma, seed, truth, shared,
         x, y, sg = alloc(total), alloc(total), alloc(total)
     grid = np.linspace(x_range[0], x_range[1], n_points)
     f = MODEL_FUNCS[model]
-    for s in range(n_sets):
-        a, b = s * n_points, (s + 1) * n_points
-        if owned is not None and s not in owned:
-            continue
+    for s in held:
+        a = (s - held.start) * n_points
+        b = a + n_points
         rng = np.random.default_rng(seed + s)
         x[a:b] = grid
         y[a:b] = f(truth[s], grid) + sigma * rng.standard_normal(n_points)
         sg[a:b] = sigma
     start = truth * 1.1 + 0.01
     return Workload(name, model, n_pars, shared, local, n_sets, n_points, x, y,
-                    sg, truth, start, 10.0, settings, f_val)
+                    sg, truth, start, 10.0, settings, f_val, held.start)
 
 
 def c2(n_sets=64, n_points=1_000_000, alloc=None, owned=None, iteration_limit=10):
