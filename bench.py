@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--points", type=int, default=0, help="points per data set (default: full size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--repeats", type=int, default=5,
+                    help="the timed K-step fit is repeated from the same start; the median is reported")
     return ap.parse_args()
 
 
@@ -64,7 +66,7 @@ class ClockSampler:
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index: int):
         self.index = index
@@ -76,7 +78,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -96,22 +98,27 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, loaded, reasons = [], [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            if len(r) < 7:
+            if len(r) < 8:
                 continue
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
+                power.append(float(r[2]))
+                loaded.append(float(r[7]) >= 50.0)
             except ValueError:
                 continue
             for name, flag in zip(names, r[3:7]):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
+        under_load = [c for c, l in zip(sm, loaded) if l] or sm
+        return {"sm_mhz": float(np.median(under_load)) if under_load else None,
                 "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "samples_under_load": int(sum(loaded)),
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------ reference (CPU)
@@ -278,30 +285,37 @@ def main_b200(args):
     barrier()
     if args.warmup > 0:
         solver.fit(w.lambda0)                      # W untimed warm-up iterations
-    # reset to the start values: the timed fit does the same work as the
-    # reference would from the same initial guess
-    for k in w.shared:
-        solver.setPar(k, float(w.start[0, k]), True)
-    for s_ in (owned if world > 1 else range(n_sets)):
-        for k in w.local:
-            solver.setPar(k, float(w.start[s_, k]), True, s_)
+    def reset_start():
+        # the timed fit does the same work as the reference would from the
+        # same initial guess
+        for k in w.shared:
+            solver.setPar(k, float(w.start[0, k]), True)
+        for s_ in (owned if world > 1 else range(n_sets)):
+            for k in w.local:
+                solver.setPar(k, float(w.start[s_, k]), True, s_)
+
     solver.settings.iteration_limit = args.steps
-    launches0 = solver.launches()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    solver.fit(w.lambda0)
-    torch.cuda.synchronize()
-    t_local = time.perf_counter() - t0
-    barrier()
+    runs = []
+    for _ in range(max(args.repeats, 1)):
+        reset_start()
+        launches0 = solver.launches()
+        barrier()
+        t0 = time.perf_counter()
+        solver.fit(w.lambda0)
+        torch.cuda.synchronize()
+        t_local = time.perf_counter() - t0
+        barrier()
+        k1_sec, k1_calls = solver.jacobianKernelTime()
+        runs.append(dict(seconds=max_over_ranks(t_local), launches=solver.launches() - launches0,
+                         k1_sec=max_over_ranks(k1_sec), k1_calls=k1_calls, tm=solver.timings(),
+                         done=solver.iterations()))
     clocks = sampler.stop()
-    seconds = max_over_ranks(t_local)
-    done = solver.iterations()
-    launches = solver.launches() - launches0
-    tm = solver.timings()
-    k1_sec, k1_calls = solver.jacobianKernelTime()
-    k1_sec = max_over_ranks(k1_sec)
+    runs.sort(key=lambda r: r["seconds"])
+    med = runs[len(runs) // 2]                      # median repeat
+    seconds, launches, k1_sec, k1_calls, tm, done = (med[k] for k in
+                                                     ("seconds", "launches", "k1_sec", "k1_calls", "tm", "done"))
     device_main = max_over_ranks(tm["main"][0])
     trials = len(solver.trace())
     accepted = [t for t in solver.trace() if t["decision"] == 0]
@@ -391,6 +405,7 @@ def main_b200(args):
                                "normal block + chi2 per trial step" if world > 1 else "single GPU",
             },
             "lm_iterations_per_s": done / seconds,
+            "repeats": {"n": len(runs), "seconds": [r["seconds"] for r in runs], "reported": "median"},
             "iterations_done": done, "trial_steps": trials, "final_chi2": chi2,
             "k1_sweep_entries_per_s": (nnz_total / world) / k1_sec * world if k1_sec > 0 else None,
             "device_seconds_main_loop": device_main,

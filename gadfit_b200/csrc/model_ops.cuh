@@ -111,6 +111,9 @@ struct ModelOpsImpl final : ModelOps
         GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(Shape::smem_bytes)));
+        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model>,
+                                             cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model>, kThreads, 0));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(

@@ -30,6 +30,8 @@ namespace gadfit_b200 {
 
 constexpr int kTile { 256 };    // points per tile == threads per CTA
 constexpr int kThreads { 256 };
+// Resident CTAs per SM the Jacobian sweep is compiled for (register cap 85)
+constexpr int kJacobianMinBlocks { 3 };
 
 struct SweepArgs
 {
@@ -192,7 +194,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, cons
 // (J_out[k * n_points + i]) for the omega sweep and getJacobian(); if
 // r_out != nullptr so are the weighted residuals.
 template <class Model>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
   k_jacobian(const SweepArgs a,
              const int loss_type,
              const int* __restrict__ slot_base,
@@ -272,6 +274,21 @@ __global__ void __launch_bounds__(kThreads)
         ++slot;
     } };
 
+    // Software pipeline: x, y, sigma of the NEXT tile are requested before the
+    // DMMA phase of the current one, so the DRAM latency hides behind it
+    double nx { 0.0 };
+    double ny { 0.0 };
+    double nsig { 1.0 };
+    const auto prefetch { [&](const int t) {
+        if (t < t1 && tid < a.tile_len[t]) {
+            const long long i { a.tile_off[t] + tid };
+            nx = a.x[i];
+            ny = a.y[i];
+            nsig = a.sig[i];
+        }
+    } };
+    prefetch(t0);
+
     for (int t = t0; t < t1; ++t) {
         const int s { a.tile_set[t] };
         if (s != cur_set) {
@@ -286,16 +303,20 @@ __global__ void __launch_bounds__(kThreads)
             cur_set = s;
         }
         const int len { a.tile_len[t] };
+        const double px { nx };
+        const double py { ny };
+        const double psig { nsig };
+        prefetch(t + 1);
         if (warp * 32 >= len) {
             continue; // nothing for this warp in a tail tile
         }
         double* column { s_A + tid };
         if (tid < len) {
             const long long i { a.tile_off[t] + tid };
-            const double inv_sig { 1.0 / a.sig[i] };
-            const auto f { Model {}(GradCtx { s_par }, a.x[i]) };
+            const double inv_sig { 1.0 / psig };
+            const auto f { Model {}(GradCtx { s_par }, px) };
             // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
-            const double res { (a.y[i] - f.val) * inv_sig };
+            const double res { (py - f.val) * inv_sig };
             const double w { loss_weight(loss_type, res) };
             const double scale { w * inv_sig };
             double g[NP];
