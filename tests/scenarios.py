@@ -1,0 +1,187 @@
+"""Fit scenarios shared by the golden-vector generator and the parity tests.
+
+C1 scenarios restate the sections of the reference's own LM-solver test file
+(reference c++/tests/lm_solver.cpp); each carries the known-answer values that
+file asserts (chi2, tau, I0-0, bgr-0, I0-1, bgr-1) with the tolerance it uses.
+C2-C5 are the BASELINE configs scaled down to sizes the dense reference can
+run.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from gadfit_b200 import workloads as W
+
+# index into fix_d (c++/tests/fixtures.h:9-17)
+I0_0, BGR_0, TAU, I0_1, BGR_1 = 0, 1, 3, 4, 5
+
+
+def _c1(name, lines, active, kat, settings=None, tol=1e-14, i0=(I0_0, I0_1), tau_name=None,
+        n_points=(100, 100)):
+    """active = (I0-0, bgr-0, I0-1, bgr-1, tau) activity flags."""
+    return dict(name=name, kind="c1", lines=lines, active=active, kat=kat, tol=tol,
+                settings=dict(iteration_limit=4) | (settings or {}), lambda0=1.0, i0=i0,
+                n_points=n_points)
+
+
+# (chi2, tau, I0-0, bgr-0, I0-1, bgr-1); None = "stays at its fixed start value"
+C1_SCENARIOS = [
+    _c1("indexing_all", "21-47", (1, 1, 1, 1, 1),
+        (11620.0867270475, 17.8650243622964, 39.77705004578393, 13.57729652858559,
+         129.0275065609783, 16.09079665934463)),
+    _c1("indexing_bgr0_bgr1", "48-64", (0, 1, 0, 1, 1),
+        (153628.8903849508, 31.95892116514992, None, 17.81484199806565, None, 36.73244337347508)),
+    _c1("indexing_I00_I01", "65-81", (1, 0, 1, 0, 1),
+        (10810.65153981582, 21.30228862988602, 56.42893238415446, None, 139.4901380914605, None)),
+    _c1("indexing_tau_only", "82-96", (0, 0, 0, 0, 1),
+        (51624.83919460665, 10.99329301695744, None, None, None, None), i0=(16, 17)),
+    _c1("indexing_bgr0_I01_bgr1", "97-114", (0, 1, 1, 1, 1),
+        (15974.61260816282, 20.47926391663428, None, 18.47600900933105, 143.0431252627765,
+         9.453915929181857)),
+    _c1("indexing_I00_bgr0_bgr1", "115-132", (1, 1, 0, 1, 1),
+        (145780.4588072044, 8.408237957600141, 45.87087327322397, 16.59126759913267, None,
+         36.38255403506549)),
+    _c1("indexing_I00_I01_bgr1", "133-150", (1, 0, 1, 1, 1),
+        (11623.17388899667, 20.61333132315124, 56.5139576021328, None, 134.8973104943701,
+         11.77612256514583)),
+    _c1("indexing_I00_bgr0_I01", "151-168", (1, 1, 1, 0, 1),
+        (30610.67204238365, 16.54682323514368, 29.98632400541692, 12.99477135618182,
+         124.6991105597198, None)),
+    _c1("indexing_I00_bgr1", "169-185", (1, 0, 0, 1, 1),
+        (150672.9869101836, 16.73368044360274, 53.73848940201638, None, None, 36.50405720192947)),
+    _c1("indexing_bgr0_I01", "186-202", (0, 1, 1, 0, 1),
+        (15348.60122706107, 21.87456778662339, None, 18.39176693290169, 147.1783948678938, None)),
+    _c1("no_iterations", "379-393", (1, 1, 1, 1, 1),
+        (284681.4650859562, 0.5356792380861322, 6.13604207015635, 2.960644474827888,
+         -1.472720596147903, 4.251266120087788), settings=dict(iteration_limit=0)),
+    _c1("no_iteration_limit", "394-411", (1, 1, 1, 1, 1),
+        (5640.175130917765, 20.85609539787557, 46.44788540145462, 10.32140443380387,
+         152.2711588123377, 5.533936911147024), settings=dict(iteration_limit=100), tol=1e-8),
+    _c1("dtd_no_constraints", "427-443", (1, 1, 1, 1, 1),
+        (5761.320550200902, 20.15808767822605, 46.33952661438988, 10.40696426744941,
+         151.8449704289686, 5.793008018375257),
+        settings=dict(iteration_limit=5, damp_max=False, DTD_min=[2.0, 1.0, 3.0, 1.0, 7.0])),
+    _c1("dtd_default", "444-457", (1, 1, 1, 1, 1),
+        (5687.451130305415, 21.01892108898218, 46.18357253310398, 10.48386354002993,
+         151.5283959798012, 6.087406702661871), settings=dict(iteration_limit=5)),
+    _c1("dtd_min", "458-472", (1, 1, 1, 1, 1),
+        (5640.44344354764, 20.8194135048056, 46.44560357121117, 10.33411834275264,
+         152.2267670731584, 5.560463422860977),
+        settings=dict(iteration_limit=5, DTD_min=[2.0, 1.0, 3.0, 1.0, 7.0])),
+    _c1("geodesic_acceleration", "475-497", (1, 1, 1, 1, 1),
+        (5641.66030550462, 20.70654799943915, 46.48065799723029, 10.39142422387268,
+         152.4514268293043, 5.748941149916498),
+        settings=dict(iteration_limit=5, acceleration_threshold=0.9)),
+    _c1("loss_linear", "512-526", (1, 1, 1, 1, 1),
+        (5687.451130305415, 21.01892108898218, 46.18357253310398, 10.48386354002993,
+         151.5283959798012, 6.087406702661871), settings=dict(iteration_limit=5, loss=0)),
+    _c1("loss_cauchy", "527-540", (1, 1, 1, 1, 1),
+        (16869.67716299524, 17.45448014750576, 40.28201426242013, 9.278480584355261,
+         132.6242198264016, 6.7051221338403), settings=dict(iteration_limit=5, loss=1)),
+    _c1("loss_huber", "541-556", (1, 1, 1, 1, 1),
+        (123695.8709974329, 4.643243104460152, 52.6348486049053, 7.874003370245958,
+         166.3872296081963, 7.690335499679898), settings=dict(iteration_limit=2, loss=2)),
+    _c1("no_degrees_of_freedom", "323-342", (1, 1, 1, 1, 1),
+        (None, 2.945868346541778, 7.351966871429338, 49.68674387147222, -13.18731292934346,
+         162.1781165060037), tol=1e-12, n_points=(3, 2)),
+]
+
+# BASELINE configs 2-5 at sizes the dense reference runs in well under a second
+SCALED_SCENARIOS = [
+    dict(name="C2_scaled", kind="workload", workload="C2", kwargs=dict(n_sets=4, n_points=2000)),
+    dict(name="C3_scaled", kind="workload", workload="C3", kwargs=dict(n_sets=8, n_points=512)),
+    dict(name="C3_scaled_40", kind="workload", workload="C3", kwargs=dict(n_sets=40, n_points=300)),
+    dict(name="C4_scaled", kind="workload", workload="C4", kwargs=dict(n_sets=4, n_points=256)),
+    dict(name="C5_scaled", kind="workload", workload="C5", kwargs=dict(n_sets=6, n_points=64)),
+    dict(name="C2_ragged", kind="workload", workload="C2", kwargs=dict(n_sets=3, n_points=777),
+         ragged=[777, 1, 300]),
+]
+
+ALL_SCENARIOS = C1_SCENARIOS + SCALED_SCENARIOS
+
+
+def build(scenario: dict, make_solver, c1_data: dict):
+    """Instantiate `scenario` on a solver produced by make_solver(model)."""
+    keep = []
+    if scenario["kind"] == "c1":
+        d = c1_data["fix_d"]
+        s = make_solver("exponential")
+        n1, n2 = scenario["n_points"]
+        x1, y1 = c1_data["x_data_1"][:n1].copy(), c1_data["y_data_1"][:n1].copy()
+        x2, y2 = c1_data["x_data_2"][:n2].copy(), c1_data["y_data_2"][:n2].copy()
+        keep += [x1, y1, x2, y2]
+        s.addDataset(x1, y1)
+        s.addDataset(x2, y2)
+        a = scenario["active"]
+        i00, i01 = scenario["i0"]
+        s.setPar(0, d[i00], bool(a[0]), 0)
+        s.setPar(2, d[BGR_0], bool(a[1]), 0)
+        s.setPar(0, d[i01], bool(a[2]), 1)
+        s.setPar(2, d[BGR_1], bool(a[3]), 1)
+        s.setPar(1, d[TAU], bool(a[4]))
+        for k, v in scenario["settings"].items():
+            setattr(s.settings, k, v)
+        lam = scenario["lambda0"]
+        n_sets, n_pars = 2, 3
+    else:
+        w = W.WORKLOADS[scenario["workload"]](**scenario["kwargs"])
+        s = make_solver(w.model)
+        if "ragged" in scenario:
+            # unequal data-set sizes (incl. a single-point set): edge case of
+            # the tile / slot bookkeeping
+            for i, n in enumerate(scenario["ragged"]):
+                xs, ys, es = w.slice(i)
+                s.addDataset(xs[:n], ys[:n], es[:n])
+            for k in w.shared:
+                s.setPar(k, float(w.start[0, k]), True)
+            for key, val in w.settings.items():
+                setattr(s.settings, key, val)
+        else:
+            w.setup(s)
+        keep.append(w)
+        lam = w.lambda0
+        n_sets, n_pars = w.n_sets, w.n_pars
+    s._scenario_keep = keep
+    return s, lam, n_sets, n_pars
+
+
+def run(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1) -> dict:
+    s, lam, n_sets, n_pars = build(scenario, make_solver, c1_data)
+    s.settings.n_threads = n_threads
+    s.fit(lam)
+    return dict(
+        name=scenario["name"],
+        chi2=s.chi2(),
+        pars=[[s.getParValue(k, i) for k in range(n_pars)] for i in range(n_sets)],
+        trace=s.trace(),
+        iterations=s.iterations(),
+        dof=s.degreesOfFreedom(),
+    ), s
+
+
+def compare_to_golden(got: dict, want: dict, rtol: float, converged_rel: float = 1e-12):
+    """Parameters and chi2 within rtol; accept/reject sequence identical up to
+    the trial where chi2 has converged to `converged_rel` (beyond that the
+    reference's own decisions are rounding noise, cf. its test comment at
+    c++/tests/lm_solver.cpp:396-398).  Returns the number of trials compared."""
+    tg, tw = got["trace"], want["trace"]
+    n_cmp = 0
+    for a, b in zip(tg, tw):
+        assert a["decision"] == b["decision"], (got["name"], n_cmp, a, b)
+        assert a["lambda_"] == b["lambda_"], (got["name"], n_cmp, a, b)
+        np.testing.assert_allclose(a["new_chi2"], b["new_chi2"], rtol=rtol)
+        n_cmp += 1
+        if abs(b["new_chi2"] - b["old_chi2"]) <= converged_rel * abs(b["old_chi2"]):
+            break
+    else:
+        assert len(tg) == len(tw), (got["name"], len(tg), len(tw))
+        assert got["iterations"] == want["iterations"]
+    converged = n_cmp < len(tw)
+    # after convergence the remaining iterations only move the parameters by
+    # rounding noise times the conditioning: compare at a looser tolerance
+    # Stated tolerance of the north star: parameters and chi2 to 1e-10 relative
+    tol = max(rtol, 1e-10) if not converged else max(rtol, 1e-7)
+    np.testing.assert_allclose(got["chi2"], want["chi2"], rtol=max(rtol, 1e-12))
+    np.testing.assert_allclose(np.array(got["pars"]), np.array(want["pars"]), rtol=tol, atol=0.0)
+    assert got["dof"] == want["dof"]
+    return n_cmp
