@@ -181,7 +181,7 @@ def run_cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 2
     }
 
 
-def main_reference(args):
+def main_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -201,12 +201,12 @@ def main_reference(args):
         "lm_iterations_per_s": base["lm_iterations_per_s"],
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------ GPU arm
 
-def main_b200(args):
+def main_b200(args, emit):
     import torch
     import torch.distributed as dist
 
@@ -244,13 +244,13 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    uid = None
-    if world > 1:
+    def fresh_uid():
+        """A NCCL unique id per communicator: rank 0 creates, everyone receives."""
         buf = torch.zeros(128, dtype=torch.uint8, device=device)
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
 
     sets_per_gpu = args.sets or SETS_PER_GPU[args.workload]
     n_points = args.points or POINTS[args.workload]
@@ -272,7 +272,7 @@ def main_b200(args):
         s = LMsolver(w.model)
         s.setDevice(local_rank)
         if world > 1:
-            s.setComm(rank, world, uid)
+            s.setComm(rank, world, fresh_uid())
         w.setup(s, owned=owned if world > 1 else None, pointers=False)
         s.settings.iteration_limit = limit
         return s
@@ -417,14 +417,21 @@ def main_b200(args):
             "e2e": e2e,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     a = parse_args()
+    # Libraries (NCCL's version banner, OpenMP notices) may write to stdout;
+    # stdout must carry exactly ONE JSON line, so everything else goes to
+    # stderr until the line is printed.
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+    _emit = lambda text: os.write(_stdout_fd, (text + "\n").encode())  # noqa: E731
     if a.impl == "reference":
-        main_reference(a)
+        main_reference(a, _emit)
     else:
-        main_b200(a)
+        main_b200(a, _emit)

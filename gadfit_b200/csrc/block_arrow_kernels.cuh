@@ -157,9 +157,11 @@ __global__ void k_local_prepare(const double* __restrict__ M,
                                 double* __restrict__ contrib,   // [n_sets][VG]
                                 const int VG)
 {
+    // One WARP per data set, lanes over the output entries (pure gather)
     constexpr int NA { NP + 1 };
     constexpr int NT { NA * (NA + 1) / 2 };
-    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    const int s { static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5) };
+    const int lane { static_cast<int>(threadIdx.x) & 31 };
     if (s >= n_sets) {
         return;
     }
@@ -169,7 +171,7 @@ __global__ void k_local_prepare(const double* __restrict__ M,
     int pg;
     int pl;
     role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
-    for (int a = 0; a < pl; ++a) {
+    for (int a = lane; a < pl; a += 32) {
         const int k { idx_l[a] };
         const double jtj { Ms[tri_index(NA, k, k)] };
         double* d { dtd_local + static_cast<long long>(s) * NP + k };
@@ -177,14 +179,19 @@ __global__ void k_local_prepare(const double* __restrict__ M,
         *d = damp_max != 0 ? ((*d < jtj) ? jtj : *d) : jtj;
     }
     double* out { contrib + static_cast<long long>(s) * VG };
-    int o { 0 };
-    for (int a = 0; a < pg; ++a) {
-        for (int b = a; b < pg; ++b) {
-            out[o++] = Ms[tri_index(NA, idx_g[a], idx_g[b])];
+    const int ntri { pg * (pg + 1) / 2 };
+    for (int o = lane; o < VG; o += 32) {
+        if (o < ntri) {
+            int a { 0 };
+            int rem { o };
+            while (rem >= pg - a) {
+                rem -= pg - a;
+                ++a;
+            }
+            out[o] = Ms[tri_index(NA, idx_g[a], idx_g[a + rem])];
+        } else {
+            out[o] = Ms[tri_index(NA, idx_g[o - ntri], NP)];
         }
-    }
-    for (int a = 0; a < pg; ++a) {
-        out[o++] = Ms[tri_index(NA, idx_g[a], NP)];
     }
 }
 
@@ -311,74 +318,109 @@ __global__ void k_local_schur_rhs(const double* __restrict__ v_sets, // [n_sets]
     }
 }
 
-// Shared-parameter system, one thread (pg <= 32).
+// Shared-parameter system on ONE WARP (pg <= 32), matrix in shared memory.
 //   shared_sums = [G (packed upper), b_g]            (once per iteration)
 //   schur_sums  = [sum Y'Y (packed upper), sum Y'z]  (per trial)
 // which == 1: factorise G + lambda D_g - sum Y'Y and solve for delta1_g
 //             (update_dtd != 0: first apply lm_solver.cpp:326-329 to D_g)
 // which == 2: reuse the factor, rhs = rhs2_sums[0..pg) - rhs2_sums[pg..2pg)
+// Lane i owns row i.  Column j of the factor is finished by all lanes at
+// once (left-looking Cholesky); every inner sum runs over k in ascending
+// order, i.e. exactly the operation order of the reference's sequential
+// dpptrf / dpptrs loops (lapack_fallback.cpp:59-105), so the result is
+// bit-identical to a one-thread implementation.
 constexpr int kMaxShared { 32 };
 
-__global__ void k_shared_solve(const int pg,
-                               const int which,
-                               const int update_dtd,
-                               const int damp_max,
-                               const double* __restrict__ shared_sums,
-                               const double* __restrict__ schur_sums,
-                               const double* __restrict__ rhs2_sums,
-                               const LmState* __restrict__ state,
-                               double* __restrict__ dtd_global, // [pg]
-                               double* __restrict__ chol,       // [pg*pg]
-                               double* __restrict__ delta_g)    // [pg]
+__global__ void __launch_bounds__(32)
+  k_shared_solve(const int pg,
+                 const int which,
+                 const int update_dtd,
+                 const int damp_max,
+                 const double* __restrict__ shared_sums,
+                 const double* __restrict__ schur_sums,
+                 const double* __restrict__ rhs2_sums,
+                 const LmState* __restrict__ state,
+                 double* __restrict__ dtd_global, // [pg]
+                 double* __restrict__ chol,       // [pg*pg]
+                 double* __restrict__ delta_g)    // [pg]
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) {
-        return;
-    }
+    __shared__ double s_L[kMaxShared][kMaxShared + 1];
+    const int lane { static_cast<int>(threadIdx.x) };
     const int ntri { pg * (pg + 1) / 2 };
+    const bool row { lane < pg };
     if (which == 1) {
         const double lambda { state->lambda };
-        if (update_dtd != 0) {
-            int o { 0 };
-            for (int a = 0; a < pg; ++a) {
-                const double jtj { shared_sums[o] };
-                const double d { dtd_global[a] };
-                dtd_global[a] = damp_max != 0 ? ((d < jtj) ? jtj : d) : jtj;
-                o += pg - a;
+        double dtd { 0.0 };
+        if (row) {
+            dtd = dtd_global[lane];
+            if (update_dtd != 0) {
+                const double jtj { shared_sums[tri_index(pg, lane, lane)] };
+                dtd = damp_max != 0 ? ((dtd < jtj) ? jtj : dtd) : jtj;
+                dtd_global[lane] = dtd;
             }
-        }
-        // Lower Cholesky, loop order of lapack_fallback.cpp:59-81
-        for (int i = 0; i < pg; ++i) {
-            for (int j = 0; j < i; ++j) {
-                const int o { tri_index(pg, j, i) };
+            // Row `lane` of the lower triangle of the damped, Schur-reduced matrix
+            for (int j = 0; j <= lane; ++j) {
+                const int o { tri_index(pg, j, lane) };
                 double v { shared_sums[o] - schur_sums[o] };
-                for (int k = 0; k < j; ++k) {
-                    v -= chol[i * pg + k] * chol[j * pg + k];
+                if (j == lane) {
+                    v = shared_sums[o] + lambda * dtd - schur_sums[o];
                 }
-                chol[i * pg + j] = v / chol[j * pg + j];
+                s_L[lane][j] = v;
             }
-            const int o { tri_index(pg, i, i) };
-            double v { shared_sums[o] + lambda * dtd_global[i] - schur_sums[o] };
-            for (int k = 0; k < i; ++k) {
-                v -= chol[i * pg + k] * chol[i * pg + k];
+        }
+        __syncwarp();
+        for (int j = 0; j < pg; ++j) {
+            double v { 0.0 };
+            if (row && lane >= j) {
+                v = s_L[lane][j];
+                for (int k = 0; k < j; ++k) {
+                    v -= s_L[lane][k] * s_L[j][k];
+                }
             }
-            chol[i * pg + i] = ::sqrt(v);
+            const double diag { ::sqrt(__shfl_sync(0xffffffffU, v, j)) };
+            if (row && lane >= j) {
+                s_L[lane][j] = lane == j ? diag : v / diag;
+            }
+            __syncwarp();
+        }
+        if (row) {
+            for (int j = 0; j <= lane; ++j) {
+                chol[lane * pg + j] = s_L[lane][j];
+            }
+        }
+    } else {
+        if (row) {
+            for (int j = 0; j <= lane; ++j) {
+                s_L[lane][j] = chol[lane * pg + j];
+            }
+        }
+        __syncwarp();
+    }
+    // Forward substitution L y = rhs
+    double v { 0.0 };
+    if (row) {
+        v = which == 1 ? shared_sums[ntri + lane] - schur_sums[ntri + lane]
+                       : rhs2_sums[lane] - rhs2_sums[pg + lane];
+    }
+    for (int j = 0; j < pg; ++j) {
+        const double yj { __shfl_sync(0xffffffffU, v, j) / s_L[j][j] };
+        if (lane == j) {
+            v = yj;
+        } else if (row && lane > j) {
+            v -= s_L[lane][j] * yj;
         }
     }
-    double y[kMaxShared];
-    for (int i = 0; i < pg; ++i) {
-        double v { which == 1 ? shared_sums[ntri + i] - schur_sums[ntri + i]
-                              : rhs2_sums[i] - rhs2_sums[pg + i] };
-        for (int j = 0; j < i; ++j) {
-            v -= chol[i * pg + j] * y[j];
-        }
-        y[i] = v / chol[i * pg + i];
-    }
+    // Backward substitution L' x = y
     for (int i = pg - 1; i >= 0; --i) {
-        double v { y[i] };
-        for (int j = pg - 1; j > i; --j) {
-            v -= chol[j * pg + i] * delta_g[j];
+        const double xi { __shfl_sync(0xffffffffU, v, i) / s_L[i][i] };
+        if (lane == i) {
+            v = xi;
+        } else if (lane < i) {
+            v -= s_L[i][lane] * xi;
         }
-        delta_g[i] = v / chol[i * pg + i];
+    }
+    if (row) {
+        delta_g[lane] = v;
     }
 }
 

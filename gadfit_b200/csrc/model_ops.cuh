@@ -186,7 +186,11 @@ struct ModelOpsImpl final : ModelOps
                        double* contrib,
                        const int VG) const -> void override
     {
-        k_local_prepare<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
+        // one warp per data set
+        k_local_prepare<NP><<<blocks_for(static_cast<long long>(n_sets) * 32, kSetThreads),
+                              kSetThreads,
+                              0,
+                              st>>>(
           M, active, global_mask, n_sets, damp_max, dtd_local, contrib, VG);
     }
     auto local_schur(cudaStream_t st,

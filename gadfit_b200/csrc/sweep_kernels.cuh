@@ -32,6 +32,8 @@ constexpr int kTile { 256 };    // points per tile == threads per CTA
 constexpr int kThreads { 256 };
 // Resident CTAs per SM the Jacobian sweep is compiled for (register cap 85)
 constexpr int kJacobianMinBlocks { 3 };
+// Tiles of one data set the chi2 sweep evaluates per loop iteration
+constexpr int kChi2Unroll { 4 };
 
 struct SweepArgs
 {
@@ -116,21 +118,53 @@ __global__ void __launch_bounds__(kThreads)
                                     * (blockIdx.x + 1) / gridDim.x) };
     double sum { 0.0 };
     int cur_set { -1 };
-    for (int t = t0; t < t1; ++t) {
+    const int tid { static_cast<int>(threadIdx.x) };
+    int t { t0 };
+    while (t < t1) {
         const int s { a.tile_set[t] };
         if (s != cur_set) {
             __syncthreads();
-            if (threadIdx.x < NP) {
-                s_par[threadIdx.x] = a.par[static_cast<long long>(s) * NP + threadIdx.x];
+            if (tid < NP) {
+                s_par[tid] = a.par[static_cast<long long>(s) * NP + tid];
             }
             __syncthreads();
             cur_set = s;
         }
-        if (static_cast<int>(threadIdx.x) < a.tile_len[t]) {
-            const long long i { a.tile_off[t] + threadIdx.x };
-            const double f { value_of(Model {}(ValueCtx { s_par }, a.x[i])) };
-            const double diff { (a.y[i] - f) / a.sig[i] };
-            sum += diff * diff;
+        if (t + kChi2Unroll <= t1 && a.tile_set[t + kChi2Unroll - 1] == s) {
+            // kChi2Unroll consecutive tiles of one data set (contiguous in
+            // memory; only the last may be partial): the loads are issued
+            // together and the unrolled evaluations share every
+            // parameter-only subexpression (1/w, ...) and constant
+            const long long base { a.tile_off[t] + tid };
+            const int last_len { a.tile_len[t + kChi2Unroll - 1] };
+            double x[kChi2Unroll];
+            double y[kChi2Unroll];
+            double sg[kChi2Unroll];
+#pragma unroll
+            for (int u = 0; u < kChi2Unroll; ++u) {
+                const bool in { u + 1 < kChi2Unroll || tid < last_len };
+                const long long i { base + u * kTile };
+                x[u] = in ? a.x[i] : 0.0;
+                y[u] = in ? a.y[i] : 0.0;
+                sg[u] = in ? a.sig[i] : 1.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kChi2Unroll; ++u) {
+                const double f { value_of(Model {}(ValueCtx { s_par }, x[u])) };
+                const double diff { (y[u] - f) / sg[u] };
+                if (u + 1 < kChi2Unroll || tid < last_len) {
+                    sum += diff * diff;
+                }
+            }
+            t += kChi2Unroll;
+        } else {
+            if (tid < a.tile_len[t]) {
+                const long long i { a.tile_off[t] + tid };
+                const double f { value_of(Model {}(ValueCtx { s_par }, a.x[i])) };
+                const double diff { (a.y[i] - f) / a.sig[i] };
+                sum += diff * diff;
+            }
+            ++t;
         }
     }
     const double total { block_sum(sum, s_red) };
