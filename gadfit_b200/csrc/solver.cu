@@ -189,9 +189,9 @@ struct SolverImpl
     std::vector<long long> local_count; // owned points of each local set
 
     DeviceBuffer<double> d_x, d_y, d_sig;
-    DeviceBuffer<int> d_tile_set, d_tile_len;
-    DeviceBuffer<long long> d_tile_off;
-    std::vector<int> h_tile_set;
+    DeviceBuffer<int> d_set_tile_begin;        // [n_local_sets + 1]
+    DeviceBuffer<long long> d_set_point_begin; // [n_local_sets + 1]
+    std::vector<int> h_tile_set;               // data set of each tile (host, for the slots)
     int n_tiles { 0 };
     SlotTable slots_jac, slots_omega;
     int grid_chi2 { 0 };
@@ -519,21 +519,17 @@ struct SolverImpl
 
         // Tiles
         h_tile_set.clear();
-        std::vector<long long> tile_off;
-        std::vector<int> tile_len;
-        long long off { 0 };
+        std::vector<int> set_tile_begin(n_local_sets + 1, 0);
+        std::vector<long long> set_point_begin(n_local_sets + 1, 0);
         for (int ls = 0; ls < n_local_sets; ++ls) {
-            for (long long p = 0; p < local_count[ls]; p += kTile) {
-                h_tile_set.push_back(ls);
-                tile_off.push_back(off + p);
-                tile_len.push_back(static_cast<int>(std::min<long long>(kTile, local_count[ls] - p)));
-            }
-            off += local_count[ls];
+            const int tiles { static_cast<int>((local_count[ls] + kTile - 1) / kTile) };
+            h_tile_set.insert(h_tile_set.end(), tiles, ls);
+            set_tile_begin[ls + 1] = set_tile_begin[ls] + tiles;
+            set_point_begin[ls + 1] = set_point_begin[ls] + local_count[ls];
         }
         n_tiles = static_cast<int>(h_tile_set.size());
-        d_tile_set.upload(h_tile_set, stream);
-        d_tile_off.upload(tile_off, stream);
-        d_tile_len.upload(tile_len, stream);
+        d_set_tile_begin.upload(set_tile_begin, stream);
+        d_set_point_begin.upload(set_point_begin, stream);
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
 
         const int sms { sm_count() };
@@ -601,8 +597,8 @@ struct SolverImpl
 
     [[nodiscard]] auto sweep_args() const -> SweepArgs
     {
-        return { d_x.ptr,        d_y.ptr,        d_sig.ptr, d_tile_set.ptr,
-                 d_tile_off.ptr, d_tile_len.ptr, n_tiles,   d_par.ptr };
+        return { d_x.ptr, d_y.ptr,      d_sig.ptr, d_set_tile_begin.ptr, d_set_point_begin.ptr,
+                 n_local_sets, n_tiles, d_par.ptr };
     }
 
     // --------------------------------------------------------------- phases

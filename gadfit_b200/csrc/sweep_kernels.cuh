@@ -6,8 +6,9 @@
 //
 // LAYOUT IN HBM.  x, y, sigma of every data set this GPU owns are concatenated
 // data-set-major into three arrays; a TILE is up to kTile consecutive points of
-// ONE data set (tile_set / tile_off / tile_len).  A CTA owns a contiguous range
-// of tiles, one thread per point, loads are fully coalesced.  Parameters of
+// ONE data set (geometry per data set: set_tile_begin / set_point_begin).  A CTA
+// owns a contiguous range of tiles, one thread per point, loads are fully
+// coalesced.  Parameters of
 // the current data set sit in shared memory.
 //
 // NORMAL EQUATIONS.  The reference stores the dense N x n Jacobian and calls
@@ -40,12 +41,82 @@ struct SweepArgs
     const double* __restrict__ x;
     const double* __restrict__ y;
     const double* __restrict__ sig;
-    const int* __restrict__ tile_set;       // data set (local index) per tile
-    const long long* __restrict__ tile_off; // first point of the tile
-    const int* __restrict__ tile_len;       // points in the tile (<= kTile)
+    // Tile geometry per DATA SET (not per tile): data set s owns the tiles
+    // [set_tile_begin[s], set_tile_begin[s+1]) and the points
+    // [set_point_begin[s], set_point_begin[s+1]) of the concatenated arrays
+    const int* __restrict__ set_tile_begin;
+    const long long* __restrict__ set_point_begin;
+    int n_sets;
     int n_tiles;
     const double* __restrict__ par; // [n_sets][NP] current parameters
 };
+
+// Walks the tiles of a CTA in ascending order.  Offsets and lengths are
+// arithmetic; memory is touched only when the data set changes.
+struct TileWalker
+{
+    int set { -1 };
+    int tile_begin { 0 };
+    int tile_end { 0 };
+    long long point_begin { 0 };
+    long long point_end { 0 };
+
+    __device__ __forceinline__ void load(const SweepArgs& a, const int s)
+    {
+        set = s;
+        tile_begin = a.set_tile_begin[s];
+        tile_end = a.set_tile_begin[s + 1];
+        point_begin = a.set_point_begin[s];
+        point_end = a.set_point_begin[s + 1];
+    }
+    // Data set that contains tile t (binary search, once per CTA)
+    __device__ __forceinline__ void seek(const SweepArgs& a, const int t)
+    {
+        int lo { 0 };
+        int hi { a.n_sets };
+        while (hi - lo > 1) {
+            const int mid { (lo + hi) >> 1 };
+            if (a.set_tile_begin[mid] <= t) {
+                lo = mid;
+            } else {
+                hi = mid;
+            }
+        }
+        load(a, lo);
+    }
+    // t must not decrease and must be < n_tiles; empty data sets are skipped
+    __device__ __forceinline__ void advance_to(const SweepArgs& a, const int t)
+    {
+        while (t >= tile_end) {
+            load(a, set + 1);
+        }
+    }
+    __device__ __forceinline__ long long off(const int t) const
+    {
+        return point_begin + static_cast<long long>(t - tile_begin) * kTile;
+    }
+    __device__ __forceinline__ int len(const int t) const
+    {
+        const long long rest { point_end - off(t) };
+        return rest < kTile ? static_cast<int>(rest) : kTile;
+    }
+};
+
+// Asynchronous 8-byte copy global -> shared (SASS: LDGSTS): no register is
+// tied up while the DRAM request is in flight
+__device__ __forceinline__ void cp_async_8(double* smem_dst, const double* gmem_src)
+{
+    const unsigned dst { static_cast<unsigned>(__cvta_generic_to_shared(smem_dst)) };
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // Packed upper triangle, row major: (i, j), i <= j, of an NA x NA matrix
 __host__ __device__ constexpr int tri_index(const int NA, const int i, const int j)
@@ -117,26 +188,30 @@ __global__ void __launch_bounds__(kThreads)
     const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
                                     * (blockIdx.x + 1) / gridDim.x) };
     double sum { 0.0 };
-    int cur_set { -1 };
     const int tid { static_cast<int>(threadIdx.x) };
+    TileWalker walk {};
+    int cur_set { -1 };
     int t { t0 };
+    if (t0 < t1) {
+        walk.seek(a, t0);
+    }
     while (t < t1) {
-        const int s { a.tile_set[t] };
-        if (s != cur_set) {
+        walk.advance_to(a, t);
+        if (walk.set != cur_set) {
             __syncthreads();
             if (tid < NP) {
-                s_par[tid] = a.par[static_cast<long long>(s) * NP + tid];
+                s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
             }
             __syncthreads();
-            cur_set = s;
+            cur_set = walk.set;
         }
-        if (t + kChi2Unroll <= t1 && a.tile_set[t + kChi2Unroll - 1] == s) {
+        const long long base { walk.off(t) + tid };
+        if (t + kChi2Unroll <= t1 && t + kChi2Unroll <= walk.tile_end) {
             // kChi2Unroll consecutive tiles of one data set (contiguous in
             // memory; only the last may be partial): the loads are issued
             // together and the unrolled evaluations share every
             // parameter-only subexpression (1/w, ...) and constant
-            const long long base { a.tile_off[t] + tid };
-            const int last_len { a.tile_len[t + kChi2Unroll - 1] };
+            const int last_len { walk.len(t + kChi2Unroll - 1) };
             double x[kChi2Unroll];
             double y[kChi2Unroll];
             double sg[kChi2Unroll];
@@ -158,10 +233,9 @@ __global__ void __launch_bounds__(kThreads)
             }
             t += kChi2Unroll;
         } else {
-            if (tid < a.tile_len[t]) {
-                const long long i { a.tile_off[t] + tid };
-                const double f { value_of(Model {}(ValueCtx { s_par }, a.x[i])) };
-                const double diff { (a.y[i] - f) / a.sig[i] };
+            if (tid < walk.len(t)) {
+                const double f { value_of(Model {}(ValueCtx { s_par }, a.x[base])) };
+                const double diff { (a.y[base] - f) / a.sig[base] };
                 sum += diff * diff;
             }
             ++t;
@@ -308,45 +382,60 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
         ++slot;
     } };
 
-    // Software pipeline: x, y, sigma of the NEXT tile are requested before the
-    // DMMA phase of the current one, so the DRAM latency hides behind it
-    double nx { 0.0 };
-    double ny { 0.0 };
-    double nsig { 1.0 };
-    const auto prefetch { [&](const int t) {
-        if (t < t1 && tid < a.tile_len[t]) {
-            const long long i { a.tile_off[t] + tid };
-            nx = a.x[i];
-            ny = a.y[i];
-            nsig = a.sig[i];
+    // Software pipeline: x, y, sigma of the NEXT tile are copied asynchronously
+    // (LDGSTS) into a double-buffered shared staging area before the current
+    // tile is evaluated, so the DRAM latency hides behind a whole tile of work
+    // without holding registers.  Every thread reads back only what it
+    // requested itself: cp.async.wait_group is the only synchronisation.
+    __shared__ double s_pre[2][3][kTile];
+    TileWalker walk {};
+    if (t0 < t1) {
+        walk.seek(a, t0);
+    }
+    const auto prefetch { [&](const TileWalker& w, const int t, const int buf) {
+        if (tid < w.len(t)) {
+            const long long i { w.off(t) + tid };
+            cp_async_8(&s_pre[buf][0][tid], a.x + i);
+            cp_async_8(&s_pre[buf][1][tid], a.y + i);
+            cp_async_8(&s_pre[buf][2][tid], a.sig + i);
         }
+        cp_async_commit();
     } };
-    prefetch(t0);
+    if (t0 < t1) {
+        prefetch(walk, t0, 0);
+    }
+    int buf { 0 };
 
-    for (int t = t0; t < t1; ++t) {
-        const int s { a.tile_set[t] };
-        if (s != cur_set) {
+    for (int t = t0; t < t1; ++t, buf ^= 1) {
+        walk.advance_to(a, t);
+        if (walk.set != cur_set) {
             if (cur_set >= 0) {
                 flush();
             }
             __syncthreads();
             if (tid < NP) {
-                s_par[tid] = a.par[static_cast<long long>(s) * NP + tid];
+                s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
             }
             __syncthreads();
-            cur_set = s;
+            cur_set = walk.set;
         }
-        const int len { a.tile_len[t] };
-        const double px { nx };
-        const double py { ny };
-        const double psig { nsig };
-        prefetch(t + 1);
+        const int len { walk.len(t) };
+        const long long tile_off { walk.off(t) };
+        cp_async_wait_all();
+        const double px { s_pre[buf][0][tid] };
+        const double py { s_pre[buf][1][tid] };
+        const double psig { s_pre[buf][2][tid] };
+        if (t + 1 < t1) {
+            TileWalker next { walk };
+            next.advance_to(a, t + 1);
+            prefetch(next, t + 1, buf ^ 1);
+        }
         if (warp * 32 >= len) {
             continue; // nothing for this warp in a tail tile
         }
         double* column { s_A + tid };
         if (tid < len) {
-            const long long i { a.tile_off[t] + tid };
+            const long long i { tile_off + tid };
             const double inv_sig { 1.0 / psig };
             const auto f { Model {}(GradCtx { s_par }, px) };
             // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
@@ -440,22 +529,26 @@ __global__ void __launch_bounds__(kThreads)
         }
         ++slot;
     } };
+    TileWalker walk {};
+    if (t0 < t1) {
+        walk.seek(a, t0);
+    }
     for (int t = t0; t < t1; ++t) {
-        const int s { a.tile_set[t] };
-        if (s != cur_set) {
+        walk.advance_to(a, t);
+        if (walk.set != cur_set) {
             if (cur_set >= 0) {
                 flush();
             }
             __syncthreads();
             if (tid < NP) {
-                s_par[tid] = a.par[static_cast<long long>(s) * NP + tid];
-                s_seed[tid] = seed[static_cast<long long>(s) * NP + tid];
+                s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
+                s_seed[tid] = seed[static_cast<long long>(walk.set) * NP + tid];
             }
             __syncthreads();
-            cur_set = s;
+            cur_set = walk.set;
         }
-        if (tid < a.tile_len[t]) {
-            const long long i { a.tile_off[t] + tid };
+        if (tid < walk.len(t)) {
+            const long long i { walk.off(t) + tid };
             const Dir2 f { Model {}(Dir2Ctx { s_par, s_seed }, a.x[i]) };
             const double omega { f.dd / a.sig[i] };
             if (omega_out != nullptr) {
