@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgadfit_b200.so")
+# GADFIT_B200_LIB: developer override to A/B two builds of the same library
+LIB_PATH = os.environ.get("GADFIT_B200_LIB") or os.path.join(_HERE, "libgadfit_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -32,7 +32,10 @@ namespace gadfit_b200 {
 constexpr int kTile { 256 };    // points per tile == threads per CTA
 constexpr int kThreads { 256 };
 // Resident CTAs per SM the Jacobian sweep is compiled for (register cap 85)
-constexpr int kJacobianMinBlocks { 3 };
+#ifndef GADFIT_JAC_MIN_BLOCKS
+#define GADFIT_JAC_MIN_BLOCKS 3
+#endif
+constexpr int kJacobianMinBlocks { GADFIT_JAC_MIN_BLOCKS };
 // Tiles of one data set the chi2 sweep evaluates per loop iteration
 constexpr int kChi2Unroll { 4 };
 
