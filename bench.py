@@ -123,16 +123,25 @@ class ClockSampler:
 
 # ------------------------------------------------------------ reference (CPU)
 
-def reference_api():
+def reference_api(use_blas: bool = False):
     """The reference's own CPU implementation, compiled from its unmodified
     sources (oracle/_ref, kind 'reference'); else the oracle's CPU restatement
     (kind 'port').  Used only as the timed CPU baseline."""
     from gadfit_b200._capi import Api
+    # the reference's optimised configuration (lapack.cpp + OpenBLAS) when it
+    # could be linked and the problem is small enough for it (n <~ 150,
+    # lapack.cpp:92); else its default in-tree linear algebra
+    blas = os.path.join(ROOT, "oracle", "_ref", "libgadfit_ref_blas.so")
     fast = os.path.join(ROOT, "oracle", "_ref", "libgadfit_ref_fast.so")
+    if use_blas and os.path.exists(blas):
+        try:
+            return Api(blas, "gadfit_ref_", product=False), "reference", "lapack.cpp + OpenBLAS 0.3.15"
+        except OSError:
+            pass
     if os.path.exists(fast):
-        return Api(fast, "gadfit_ref_", product=False), "reference"
+        return Api(fast, "gadfit_ref_", product=False), "reference", "in-tree lapack_fallback.cpp"
     port = os.path.join(ROOT, "oracle", "_build", "libgadfit_oracle.so")
-    return Api(port, "gadfit_oracle_", product=False), "port"
+    return Api(port, "gadfit_oracle_", product=False), "port", "oracle restatement"
 
 
 def run_cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 20.0) -> dict:
@@ -143,7 +152,7 @@ def run_cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 2
     from gadfit_b200 import workloads as W
     from gadfit_b200.lm_solver import LMsolver
 
-    api, kind = reference_api()
+    api, kind, linalg = reference_api(use_blas=(workload == "C2"))
     cores = os.cpu_count() or 1
     full_sets, full_points = SETS_PER_GPU[workload], POINTS[workload]
     # the dense reference is limited by n = p_g + S p_l
@@ -174,7 +183,7 @@ def run_cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 2
     return {
         "value": value, "unit": "jacobian_entries/s", "cores": cores, "kind": kind,
         "sample": f"{workload} model/settings, {sets} data sets x {points} points, {done} LM iterations, "
-                  f"all {cores} host threads (OpenMP), in-tree linear algebra",
+                  f"all {cores} host threads (OpenMP), {linalg}, g++ -O3 -march=x86-64-v3",
         "lm_iterations_per_s": done / dt,
         "jacobian_sweep_entries_per_s": w.nnz_jacobian / jac_sweep if jac_sweep > 0 else None,
         "seconds": dt,

@@ -90,8 +90,9 @@ class Api:
             raise FileNotFoundError(
                 f"{path} is missing: build it with `python -c 'import "
                 f"__graft_entry__ as g; g.build()'` (there is no CPU fallback)")
-        mode = getattr(os, "RTLD_NOW", 2) | getattr(os, "RTLD_GLOBAL", 0)
-        self.lib = C.CDLL(path, mode=mode)
+        # RTLD_LOCAL: the oracle libraries export C++ symbols of the reference
+        # that must not interpose each other
+        self.lib = C.CDLL(path, mode=getattr(os, "RTLD_NOW", 2) | getattr(os, "RTLD_LOCAL", 0))
         self.path = path
         self.prefix = prefix
         self.product = product
