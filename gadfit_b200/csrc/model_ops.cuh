@@ -108,16 +108,22 @@ struct ModelOpsImpl final : ModelOps
         if (device_ready) {
             return;
         }
-        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model>,
+        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(Shape::smem_bytes)));
-        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model>,
+        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(Shape::smem_bytes)));
+        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model, true>,
+                                             cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
+        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model, false>,
                                              cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model>, kThreads, 0));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &occupancy[1], k_jacobian<Model>, kThreads, Shape::smem_bytes));
+          &occupancy[1], k_jacobian<Model, true>, kThreads, Shape::smem_bytes));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[2], k_omega<Model>, kThreads, 0));
         for (int& o : occupancy) {
@@ -152,8 +158,13 @@ struct ModelOpsImpl final : ModelOps
                   double* r_out,
                   const long long n_points) const -> void override
     {
-        k_jacobian<Model><<<grid, kThreads, Shape::smem_bytes, st>>>(
-          a, loss, slot_base, partials, J_out, r_out, n_points);
+        if (J_out != nullptr || r_out != nullptr) {
+            k_jacobian<Model, true><<<grid, kThreads, Shape::smem_bytes, st>>>(
+              a, loss, slot_base, partials, J_out, r_out, n_points);
+        } else {
+            k_jacobian<Model, false><<<grid, kThreads, Shape::smem_bytes, st>>>(
+              a, loss, slot_base, partials, nullptr, nullptr, n_points);
+        }
     }
     auto omega(const int grid,
                cudaStream_t st,

@@ -304,7 +304,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, cons
 // If J_out != nullptr the weighted Jacobian rows are stored parameter-major
 // (J_out[k * n_points + i]) for the omega sweep and getJacobian(); if
 // r_out != nullptr so are the weighted residuals.
-template <class Model>
+// kStore: also write the weighted rows / residuals (J_out, r_out); the plain
+// instantiation carries neither the pointers nor the branches.
+template <class Model, bool kStore>
 __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
   k_jacobian(const SweepArgs a,
              const int loss_type,
@@ -451,13 +453,17 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
             for (int k = 0; k < NP; ++k) {
                 const double jk { g[k] * scale };
                 column[k * LDP] = jk;
-                if (J_out != nullptr) {
-                    J_out[static_cast<long long>(k) * n_points + i] = jk;
+                if constexpr (kStore) {
+                    if (J_out != nullptr) {
+                        J_out[static_cast<long long>(k) * n_points + i] = jk;
+                    }
                 }
             }
             column[NP * LDP] = w * res;
-            if (r_out != nullptr) {
-                r_out[i] = w * res;
+            if constexpr (kStore) {
+                if (r_out != nullptr) {
+                    r_out[i] = w * res;
+                }
             }
         } else {
 #pragma unroll

@@ -17,7 +17,9 @@
 //             d = delta1[column], dd = 0         fit_function.cpp:45-51)
 //
 // c.kronrod(...) / c.kronrod2d(...) give the fixed 15-point Kronrod panel of
-// the reference (numerical_integration.cpp:133-148,189-215).
+// the reference (numerical_integration.cpp:133-148,189-215);
+// c.integrate(lower, upper, f(ctx, t), rel_error) its adaptive G7/K15
+// integrator incl. AD-valued bounds (numerical_integration.cpp:242-423).
 #pragma once
 
 #include "dual.h"
@@ -48,6 +50,16 @@ struct ValueCtx : QuadratureMixin
 {
     const double* p;
     GADFIT_HD explicit ValueCtx(const double* p) : p { p } {}
+    GADFIT_HD ValueCtx passive() const { return *this; }
+    template <class BL, class BU, class F>
+    GADFIT_HD auto integrate(const BL& lower,
+                             const BU& upper,
+                             F&& f,
+                             const double rel_error = k_default_rel_error,
+                             const double abs_error = 0.0) const
+    {
+        return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+    }
     template <int K>
     GADFIT_HD Passive get() const
     {
@@ -59,6 +71,16 @@ struct GradCtx : QuadratureMixin
 {
     const double* p;
     GADFIT_HD explicit GradCtx(const double* p) : p { p } {}
+    GADFIT_HD ValueCtx passive() const { return ValueCtx { p }; }
+    template <class BL, class BU, class F>
+    GADFIT_HD auto integrate(const BL& lower,
+                             const BU& upper,
+                             F&& f,
+                             const double rel_error = k_default_rel_error,
+                             const double abs_error = 0.0) const
+    {
+        return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+    }
     template <int K>
     GADFIT_HD SDual<(1U << K)> get() const
     {
@@ -76,6 +98,16 @@ struct Dir2Ctx : QuadratureMixin
     const double* seed;
     GADFIT_HD Dir2Ctx(const double* p, const double* seed) : p { p }, seed { seed }
     {}
+    GADFIT_HD ValueCtx passive() const { return ValueCtx { p }; }
+    template <class BL, class BU, class F>
+    GADFIT_HD auto integrate(const BL& lower,
+                             const BU& upper,
+                             F&& f,
+                             const double rel_error = k_default_rel_error,
+                             const double abs_error = 0.0) const
+    {
+        return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+    }
     template <int K>
     GADFIT_HD Dir2 get() const
     {

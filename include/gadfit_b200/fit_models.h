@@ -15,6 +15,7 @@
 //   gauss_linear_bg      A e^{-u^2}(1+s u)+b0+b1 x       [A, mu, w, s, b0, b1]
 //   conv_exp_gauss       single-integral model           [A, tau, sg, t0, bgr]
 //   lorentz_double_int   double-integral model           [A, x0, gamma, b, c, k1, k2]
+//   single_integral_*    the reference's adaptive-integration test functions [p0, p1]
 #pragma once
 
 #include "fit_function.h"
@@ -130,6 +131,68 @@ struct LorentzDoubleInt
     }
 };
 
+// The reference's own adaptive-integration test functions ("Single integral",
+// reference c++/tests/numerical_integration.cpp:25-223): eight combinations of
+// constant / data-dependent / parameter-dependent integration bounds, with and
+// without fitting parameters inside the integrand.  Parameters [p0, p1]; the
+// constants are fix_d[0..2] of c++/tests/fixtures.h:9-11.
+//   BOUND codes: 0 = 0.0, 1 = p0 / fix_d[0], 2 = p1, 3 = the data point x
+//   INTEGRAND 0: t^p0 exp(-p1 t^2)          (:29-31)
+//             1: x t^p0 exp(-p1 t^2)        (:46-48)
+//             2: x t^fix_d[2] exp(-t^2)     (:74-76)
+template <int ID, int LOWER, int UPPER, int INTEGRAND, int SIGN>
+struct SingleIntegral
+{
+    static constexpr int n_pars { 2 };
+    static constexpr double f0 { 6.1360420701563498 };
+    static constexpr double f1 { 2.9606444748278875 };
+    static constexpr double f2 { 9.9253736972586246 };
+    static constexpr const char* names[8] {
+        "single_integral_no_bounds",        "single_integral_lower",
+        "single_integral_lower_nopar",      "single_integral_upper",
+        "single_integral_upper_nopar",      "single_integral_both",
+        "single_integral_both_lower_fixed", "single_integral_both_nopar"
+    };
+    static constexpr const char* name { names[ID] };
+
+    template <int CODE, class Ctx>
+    GADFIT_HD static auto bound(const Ctx& c, const double x)
+    {
+        if constexpr (CODE == 0) {
+            return 0.0;
+        } else if constexpr (CODE == 1) {
+            return par<0>(c) / f0;
+        } else if constexpr (CODE == 2) {
+            return par<1>(c);
+        } else {
+            return x;
+        }
+    }
+
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto integrand { [x](const auto& cc, const auto& t) {
+            if constexpr (INTEGRAND == 0) {
+                return pow(t, par<0>(cc)) * exp(-par<1>(cc) * t * t);
+            } else if constexpr (INTEGRAND == 1) {
+                return x * pow(t, par<0>(cc)) * exp(-par<1>(cc) * t * t);
+            } else {
+                return x * pow(t, f2) * exp(-t * t);
+            }
+        } };
+        return (SIGN * f1) * c.integrate(bound<LOWER>(c, x), bound<UPPER>(c, x), integrand, 1e-12);
+    }
+};
+using SingleIntegral1 = SingleIntegral<0, 0, 3, 0, 1>;  // :25-45
+using SingleIntegral2 = SingleIntegral<1, 1, 0, 1, -1>; // :46-72
+using SingleIntegral3 = SingleIntegral<2, 1, 0, 2, -1>; // :73-95
+using SingleIntegral4 = SingleIntegral<3, 0, 1, 1, 1>;  // :96-123
+using SingleIntegral5 = SingleIntegral<4, 0, 1, 2, 1>;  // :124-147
+using SingleIntegral6 = SingleIntegral<5, 1, 2, 1, -1>; // :148-175
+using SingleIntegral7 = SingleIntegral<6, 2, 1, 1, -1>; // :176-199
+using SingleIntegral8 = SingleIntegral<7, 1, 2, 2, -1>; // :200-222
+
 // Calls f.template operator()<Model>() for every registered model; the
 // library, the reference harness and the oracle all dispatch through this
 // one list.
@@ -141,6 +204,14 @@ inline void for_each_model(F&& f)
     f.template operator()<GaussLinearBg>();
     f.template operator()<ConvExpGauss>();
     f.template operator()<LorentzDoubleInt>();
+    f.template operator()<SingleIntegral1>();
+    f.template operator()<SingleIntegral2>();
+    f.template operator()<SingleIntegral3>();
+    f.template operator()<SingleIntegral4>();
+    f.template operator()<SingleIntegral5>();
+    f.template operator()<SingleIntegral6>();
+    f.template operator()<SingleIntegral7>();
+    f.template operator()<SingleIntegral8>();
 }
 
 } // namespace gadfit_b200::models

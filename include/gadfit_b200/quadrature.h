@@ -120,4 +120,171 @@ GADFIT_HD auto kronrod2d(const double outer_lower,
     return outer_scale * inner_scale * sum;
 }
 
+
+// ===========================================================================
+// Adaptive Gauss-Kronrod (G7/K15) integration, 1-D
+// ===========================================================================
+//
+// Counterpart of gadfit::integrate() (reference
+// c++/gadfit/numerical_integration.cpp:242-306): G7/K15 on [a, b], then
+// repeatedly bisect the panel with the largest error estimate (always at
+// least once) until  sum(err) < abs_error  or  sum(err)/sum(K15) < rel_error,
+// with PASSIVE parameters; finally every panel is re-evaluated with AD on by
+// the fixed rule above, in panel order (:292-298).  AD-valued bounds add the
+// Leibniz terms of traceRecordLower / traceRecordUpper (:313-376).
+//
+// The integrand is a callable f(ctx, t): it receives the evaluation context
+// (passive during refinement, the caller's during the final pass) exactly as
+// the reference hands its integrand either `inactive_parameters` or
+// `parameters`.
+//
+// The per-thread panel workspace is a fixed array (the reference's default
+// is 1000 panels on the heap, numerical_integration.h:40); overflow returns
+// NaN -- which the LM loop treats as a rejected step -- instead of throwing
+// InsufficientIntegrationWorkspace.
+
+constexpr int k_max_panels { 96 };
+constexpr double k_default_rel_error { 2.220446049250313e-14 }; // 1e2 * epsilon, numerical_integration.h:37-38
+
+#define GADFIT_G7_WEIGHTS                                                      \
+    0.129484966168869693270611432679082, 0.279705391489276667901467771423780,  \
+      0.381830050505118944950369775488975,                                     \
+      0.417959183673469387755102040816327,                                     \
+      0.129484966168869693270611432679082,                                     \
+      0.279705391489276667901467771423780,                                     \
+      0.381830050505118944950369775488975
+#if defined(__CUDACC__)
+static __constant__ double g7_weights_dev[7] { GADFIT_G7_WEIGHTS };
+#endif
+static constexpr double g7_weights_host[7] { GADFIT_G7_WEIGHTS };
+
+GADFIT_HD double g7_weight(const int i)
+{
+#if defined(__CUDA_ARCH__)
+    return g7_weights_dev[i];
+#else
+    return g7_weights_host[i];
+#endif
+}
+
+// numerical_integration.cpp:108-131: K15 value and |K15 - G7| of one panel
+template <class Ctx, class F>
+GADFIT_HD double gauss_kronrod(const Ctx& passive_ctx,
+                               F&& f,
+                               const double lower,
+                               const double upper,
+                               double& abs_error)
+{
+    const double scale { (upper - lower) / 2 };
+    const double shift { (lower + upper) / 2 };
+    double sum_kronrod { 0.0 };
+    double sum_gauss { 0.0 };
+#pragma unroll 1
+    for (int i = 0; i < k15_size; ++i) {
+        const double val { value_of(f(passive_ctx, Passive { scale * k15_root(i) + shift })) };
+        sum_kronrod += k15_weight(i) * val;
+        if (i % 2 == 1) {
+            sum_gauss += g7_weight(i / 2) * val;
+        }
+    }
+    sum_kronrod *= scale;
+    abs_error = ::fabs(sum_kronrod - scale * sum_gauss);
+    return sum_kronrod;
+}
+
+GADFIT_HD double d_of(const double) { return 0.0; }
+GADFIT_HD double d_of(const Passive&) { return 0.0; }
+GADFIT_HD double d_of(const Dir2& x) { return x.d; }
+GADFIT_HD Dir2 as_dir2(const Passive& x) { return Dir2 { x.val, 0.0, 0.0 }; }
+GADFIT_HD Dir2 as_dir2(const Dir2& x) { return x; }
+
+template <class T>
+struct is_passive_bound : std::bool_constant<std::is_arithmetic_v<T> || std::is_same_v<T, Passive>>
+{};
+
+GADFIT_HD double bound_value(const double x) { return x; }
+template <uint32_t M>
+GADFIT_HD double bound_value(const SDual<M>& x) { return x.val; }
+GADFIT_HD double bound_value(const Dir2& x) { return x.val; }
+
+// Leibniz term of one AD-valued bound; sign = +1 upper, -1 lower
+template <class Ctx, class F, class R, class B>
+GADFIT_HD auto leibniz(const Ctx& c, F&& f, const R& result, const B& bound, const double sign)
+{
+    if constexpr (is_passive_bound<B>::value) {
+        return result;
+    } else if constexpr (std::is_same_v<B, Dir2>) {
+        // numerical_integration.cpp:336-343 / :369-376
+        const auto tmp { f(c, Passive { bound.val }) };
+        Dir2 r { as_dir2(result) };
+        r.d += sign * bound.d * value_of(tmp);
+        r.dd += sign * (bound.dd * value_of(tmp) + bound.d * (d_of(f(c, bound)) + d_of(tmp)));
+        return r;
+    } else {
+        // first derivatives only: d/dp int^{b(p)} f = b'(p) f(b)
+        // (the adjoint rule of Op::integration_bound,
+        // automatic_differentiation.cpp:867-871)
+        const double fb { value_of(f(c.passive(), Passive { bound.val })) };
+        return result + (bound - bound.val) * (sign * fb);
+    }
+}
+
+template <class Ctx, class F, class BL, class BU>
+GADFIT_HD auto integrate(const Ctx& c,
+                         const BL& lower_bound,
+                         const BU& upper_bound,
+                         F&& f,
+                         const double rel_error = k_default_rel_error,
+                         const double abs_error = 0.0)
+{
+    const double lower { bound_value(lower_bound) };
+    const double upper { bound_value(upper_bound) };
+    const auto pc { c.passive() };
+    double lo[k_max_panels];
+    double hi[k_max_panels];
+    double sums[k_max_panels];
+    double errs[k_max_panels];
+    lo[0] = lower;
+    hi[0] = upper;
+    sums[0] = gauss_kronrod(pc, f, lower, upper, errs[0]);
+    int n_panels { 0 };
+    for (int iter = 0; iter + 1 < k_max_panels; ++iter) {
+        // first panel with the largest error (std::max_element)
+        int worst { 0 };
+        for (int i = 1; i <= iter; ++i) {
+            if (errs[worst] < errs[i]) {
+                worst = i;
+            }
+        }
+        const double a { lo[worst] };
+        const double b { hi[worst] };
+        const double middle { (b + a) / 2 };
+        sums[worst] = gauss_kronrod(pc, f, a, middle, errs[worst]);
+        sums[iter + 1] = gauss_kronrod(pc, f, middle, b, errs[iter + 1]);
+        hi[worst] = middle;
+        lo[iter + 1] = middle;
+        hi[iter + 1] = b;
+        double errors_sum { 0.0 };
+        double sums_sum { 0.0 };
+        for (int i = 0; i < iter + 2; ++i) {
+            errors_sum += errs[i];
+            sums_sum += sums[i];
+        }
+        if (errors_sum < abs_error || errors_sum / sums_sum < rel_error) {
+            n_panels = iter + 2;
+            break;
+        }
+    }
+    // Final pass with AD on (:292-298); the sum starts from a passive zero
+    auto result { Passive { 0.0 } + kronrod(lo[0], hi[0], [&](const Passive& t) { return f(c, t); }) };
+    for (int i = 1; i < n_panels; ++i) {
+        result = result + kronrod(lo[i], hi[i], [&](const Passive& t) { return f(c, t); });
+    }
+    if (n_panels == 0) {
+        // workspace exhausted: poison the value (=> the step is rejected)
+        result = result * (0.0 / 0.0);
+    }
+    return leibniz(c, f, leibniz(c, f, result, lower_bound, -1.0), upper_bound, 1.0);
+}
+
 } // namespace gadfit_b200

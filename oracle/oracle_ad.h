@@ -323,16 +323,138 @@ auto kronrod2d(const double outer_lower,
     return outer_scale * inner_scale * sum;
 }
 
+inline constexpr double g7_weights[7] {
+    0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+    0.381830050505118944950369775488975, 0.417959183673469387755102040816327,
+    0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+    0.381830050505118944950369775488975
+};
+
+// G7/K15 of one panel with passive parameters, numerical_integration.cpp:108-131
+template <class F>
+auto gaussKronrod(F&& f, const double lower, const double upper, double& abs_error) -> double
+{
+    const double scale { (upper - lower) / 2 };
+    const double shift { (lower + upper) / 2 };
+    double sum_kronrod {};
+    double sum_gauss {};
+    for (int i = 0; i < 15; ++i) {
+        const double val { f(passive(scale * k15_roots[i] + shift)).val };
+        sum_kronrod += k15_weights[i] * val;
+        if (i % 2 == 1) {
+            sum_gauss += g7_weights[i / 2] * val;
+        }
+    }
+    sum_kronrod *= scale;
+    abs_error = std::abs(sum_kronrod - scale * sum_gauss);
+    return sum_kronrod;
+}
+
 // Evaluation context over a parameter vector of FVar (the role the
 // std::vector<AdVar> argument plays in the reference's fitSignature,
 // fit_function.h:27-28)
 struct Ctx
 {
     const FVar* pars;
+    int n_pars { 0 };
     template <int K>
     auto get() const -> const FVar&
     {
         return pars[K];
+    }
+    // Adaptive integration, numerical_integration.cpp:242-306, and the
+    // forward-mode Leibniz terms of AD-valued bounds, :336-343 / :369-376.
+    // f(ctx, t) receives the passive copy of the parameters during refinement
+    // (setInactiveParameters, :221-240) and the caller's for the final pass.
+    template <class F>
+    auto integrate(const double lower,
+                   const double upper,
+                   F&& f,
+                   const double rel_error = 2.220446049250313e-14,
+                   const double abs_error = 0.0) const -> FVar
+    {
+        FVar inactive[64];
+        for (int i = 0; i < n_pars; ++i) {
+            inactive[i] = passive(pars[i].val);
+        }
+        const Ctx pc { inactive, n_pars };
+        const auto fp { [&](const FVar& t) { return f(pc, t); } };
+        constexpr int workspace { 1000 }; // numerical_integration.h:40
+        double lo[workspace + 1];
+        double hi[workspace + 1];
+        double sums[workspace + 1];
+        double errs[workspace + 1];
+        lo[0] = lower;
+        hi[0] = upper;
+        sums[0] = gaussKronrod(fp, lower, upper, errs[0]);
+        for (int iter = 0; iter < workspace; ++iter) {
+            int worst { 0 };
+            for (int i = 1; i <= iter; ++i) {
+                if (errs[worst] < errs[i]) {
+                    worst = i;
+                }
+            }
+            const double a { lo[worst] };
+            const double b { hi[worst] };
+            const double middle { (b + a) / 2 };
+            sums[worst] = gaussKronrod(fp, a, middle, errs[worst]);
+            sums[iter + 1] = gaussKronrod(fp, middle, b, errs[iter + 1]);
+            hi[worst] = middle;
+            lo[iter + 1] = middle;
+            hi[iter + 1] = b;
+            double errors_sum {};
+            double sums_sum {};
+            for (int i = 0; i < iter + 2; ++i) {
+                errors_sum += errs[i];
+                sums_sum += sums[i];
+            }
+            if (errors_sum < abs_error || errors_sum / sums_sum < rel_error) {
+                FVar result { passive(0.0) };
+                for (int i = 0; i < iter + 2; ++i) {
+                    result = result
+                             + gadfit_oracle::kronrod(
+                               lo[i], hi[i], [&](const FVar& t) { return f(*this, t); });
+                }
+                return result;
+            }
+        }
+        return passive(std::nan(""));
+    }
+    template <class F>
+    auto bound_term(F&& f, const FVar& bound, const double sign, FVar& result) const -> void
+    {
+        if (!bound.on) {
+            return;
+        }
+        const FVar tmp { f(*this, passive(bound.val)) };
+        result.d += sign * bound.d * tmp.val;
+        result.dd += sign * (bound.dd * tmp.val + bound.d * (f(*this, bound).d + tmp.d));
+        result.on = true;
+    }
+    template <class F>
+    auto integrate(const FVar& lower, const double upper, F&& f, const double rel = 2.220446049250313e-14,
+                   const double abs = 0.0) const -> FVar
+    {
+        FVar result { integrate(lower.val, upper, f, rel, abs) };
+        bound_term(f, lower, -1.0, result);
+        return result;
+    }
+    template <class F>
+    auto integrate(const double lower, const FVar& upper, F&& f, const double rel = 2.220446049250313e-14,
+                   const double abs = 0.0) const -> FVar
+    {
+        FVar result { integrate(lower, upper.val, f, rel, abs) };
+        bound_term(f, upper, 1.0, result);
+        return result;
+    }
+    template <class F>
+    auto integrate(const FVar& lower, const FVar& upper, F&& f, const double rel = 2.220446049250313e-14,
+                   const double abs = 0.0) const -> FVar
+    {
+        FVar result { integrate(lower.val, upper.val, f, rel, abs) };
+        bound_term(f, lower, -1.0, result);
+        bound_term(f, upper, 1.0, result);
+        return result;
     }
     template <class F>
     auto kronrod(const double lower, const double upper, F&& f) const -> FVar

@@ -56,6 +56,24 @@ struct RefCtx
           lower,
           upper);
     }
+    // gadfit::integrate, numerical_integration.h:83-113 (double or AdVar bounds)
+    template <class BL, class BU, class F>
+    auto integrate(const BL& lower,
+                   const BU& upper,
+                   F&& f,
+                   const double rel_error = gadfit::default_rel_error,
+                   const double abs_error = 0.0) const -> gadfit::AdVar
+    {
+        return gadfit::integrate(
+          [&f](const std::vector<gadfit::AdVar>& p, const gadfit::AdVar& t) {
+              return gadfit::AdVar { f(RefCtx { p }, t) };
+          },
+          pars,
+          lower,
+          upper,
+          rel_error,
+          abs_error);
+    }
     template <class F>
     auto kronrod2d(const double outer_lower,
                    const double outer_upper,

@@ -20,7 +20,8 @@ def array(src: str, name: str) -> list:
 
 if __name__ == "__main__":
     src = open(SRC).read()
-    names = ["fix_d", "x_data_1", "y_data_1", "x_data_2", "y_data_2"]
+    names = ["fix_d", "x_data_1", "y_data_1", "x_data_2", "y_data_2",
+             "x_data_single", "y_data_single"]  # fixtures.h:72-154: integration tests
     out = {n: array(src, n) for n in names}
     out["_source"] = "reference c++/tests/fixtures.h:9-68"
     json.dump(out, open(OUT, "w"))

@@ -97,6 +97,59 @@ SCALED_SCENARIOS = [
          ragged=[777, 1, 300]),
 ]
 
+# The reference's adaptive-integration tests, "Single integral"
+# (c++/tests/numerical_integration.cpp:13-223): one data set of 150 points,
+# p0 = 10, p1 = 1, iteration_limit 4, acceleration 0.9, fit(10.0).  `fits` is
+# the list of consecutive fits: (p1 active?, KAT chi2, KAT p0, KAT p1).
+INTEGRATION_SCENARIOS = [
+    dict(name="single_integral_no_bounds", lines="25-45",
+         fits=[(True, 4994.801048103614, 9.345693397983833, 1.086341822060304)]),
+    dict(name="single_integral_lower", lines="46-72",
+         fits=[(False, 3359.402760955073, 9.638686516377437, 1.0),
+               (True, 3359.360525697878, 9.63837358508365, 1.000164288516688)]),
+    dict(name="single_integral_lower_nopar", lines="73-95",
+         fits=[(False, 3359.374808601714, 9.513801290676248, 1.0)]),
+    dict(name="single_integral_upper", lines="96-123",
+         fits=[(False, 3359.402760955071, 9.638686516377437, 1.0),
+               (True, 3359.360525697879, 9.638373585083652, 1.000164288516688)]),
+    dict(name="single_integral_upper_nopar", lines="124-147",
+         fits=[(False, 3359.374808601714, 9.513801290676248, 1.0)]),
+    dict(name="single_integral_both", lines="148-175",
+         fits=[(False, 3359.392136789901, 9.664371097350363, 1.0),
+               (True, 3359.360525697834, 9.664108472227593, 1.000124158231295)]),
+    dict(name="single_integral_both_lower_fixed", lines="176-199",
+         fits=[(False, 96283.63738642586, 4.023936467213234, 1.0)]),
+    dict(name="single_integral_both_nopar", lines="200-222",
+         fits=[(True, 3359.360587615625, 9.834021674777725, 1.301193106585963)]),
+]
+for _sc in INTEGRATION_SCENARIOS:
+    _sc["kind"] = "integration"
+
+
+def run_integration(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1) -> list:
+    """Runs the consecutive fits of one "Single integral" section; returns one
+    record per fit (the second fit warm-starts from the first, as in the
+    reference test)."""
+    s = make_solver(scenario["name"])
+    x = c1_data["x_data_single"].copy()
+    y = c1_data["y_data_single"].copy()
+    s._scenario_keep = [x, y]
+    s.addDataset(x, y)
+    s.setPar(0, 10.0, True)
+    s.setPar(1, 1.0, True)
+    s.settings.iteration_limit = 4
+    s.settings.acceleration_threshold = 0.9
+    s.settings.n_threads = n_threads
+    out = []
+    for p1_active, *_ in scenario["fits"]:
+        s.setPar(1, 1.0, p1_active)  # numerical_integration.cpp:61,67
+        s.fit(10.0)
+        out.append(dict(name=scenario["name"], chi2=s.chi2(),
+                        pars=[[s.getParValue(0), s.getParValue(1)]], trace=s.trace(),
+                        iterations=s.iterations(), dof=s.degreesOfFreedom()))
+    return out
+
+
 ALL_SCENARIOS = C1_SCENARIOS + SCALED_SCENARIOS
 
 

@@ -26,8 +26,12 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_model_registry():
-    assert g.models() == {"exponential": 3, "gauss_hermite3": 20, "gauss_linear_bg": 6,
-                          "conv_exp_gauss": 5, "lorentz_double_int": 7}
+    registered = g.models()
+    for name, n_pars in {"exponential": 3, "gauss_hermite3": 20, "gauss_linear_bg": 6,
+                         "conv_exp_gauss": 5, "lorentz_double_int": 7}.items():
+        assert registered[name] == n_pars
+    singles = {k: v for k, v in registered.items() if k.startswith("single_integral_")}
+    assert len(singles) == 8 and set(singles.values()) == {2}
     with pytest.raises(g.UnknownModel):
         g.LMsolver("no_such_function")
 
