@@ -193,6 +193,67 @@ using SingleIntegral6 = SingleIntegral<5, 1, 2, 1, -1>; // :148-175
 using SingleIntegral7 = SingleIntegral<6, 2, 1, 1, -1>; // :176-199
 using SingleIntegral8 = SingleIntegral<7, 1, 2, 2, -1>; // :200-222
 
+// The reference's nested double-integral test function ("Double integral
+// (nested)", reference c++/tests/numerical_integration.cpp:240-918): an
+// adaptive integral whose integrand contains another adaptive integral, with
+// fitting parameters in all four bounds.  Parameters [p0 .. p5]:
+//   f(x) = 1/x * int_{OL}^{OH} e^{-u} [ int_{IL}^{IH} log((e^t - 0.9) q(u) + 1)/t dt ] du,
+//   q(u) = 1 + p0 p1 erf(u)
+// Bound codes -- inner: 0 = p4, 1 = p5 x / p1;  outer: 0 = p4 (p1 - p2), 1 = p3,
+// 2 = p4 p2, 3 = p3 / p5.  (In the reference test the outer integrand sees the
+// renamed vector pars2 = [p0, p1, x, p4, p5].)
+template <int ID, int IL, int IH, int OL, int OH>
+struct NestedIntegral
+{
+    static constexpr int n_pars { 6 };
+    static constexpr double tol_inner { 1e-3 };
+    static constexpr double tol_outer { 1e-2 };
+    static constexpr const char* names[3] { "nested_integral_y1y2x1x2", "nested_integral_x1x2",
+                                            "nested_integral_no_active_bounds" };
+    static constexpr const char* name { names[ID] };
+
+    template <int CODE, class Ctx>
+    GADFIT_HD static auto inner_bound(const Ctx& c, const double x)
+    {
+        if constexpr (CODE == 0) {
+            return par<4>(c);
+        } else {
+            return par<5>(c) * x / par<1>(c);
+        }
+    }
+    template <int CODE, class Ctx>
+    GADFIT_HD static auto outer_bound(const Ctx& c)
+    {
+        if constexpr (CODE == 0) {
+            return par<4>(c) * (par<1>(c) - par<2>(c));
+        } else if constexpr (CODE == 1) {
+            return par<3>(c);
+        } else if constexpr (CODE == 2) {
+            return par<4>(c) * par<2>(c);
+        } else {
+            return par<3>(c) / par<5>(c);
+        }
+    }
+
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto outer { [x](const auto& co, const auto& u) {
+            // :258-266: the inner integrand's only parameter is q(u)
+            const auto inner { [&u](const auto& ci, const auto& t) {
+                const auto q { 1 + par<0>(ci) * par<1>(ci) * erf(u) };
+                return log((exp(t) - 0.9) * q + 1.0) / t;
+            } };
+            return exp(-u)
+                   * co.integrate(inner_bound<IL>(co, x), inner_bound<IH>(co, x), inner, tol_inner);
+        } };
+        return c.integrate(outer_bound<OL>(c), outer_bound<OH>(c), outer, tol_outer) / x;
+    }
+};
+using NestedIntegral1 = NestedIntegral<0, 0, 1, 0, 1>; // :249-291  y1 y2 x1 x2
+using NestedIntegral2 = NestedIntegral<1, 0, 1, 2, 1>; // :505-547  x1 x2
+using NestedIntegral3 = NestedIntegral<2, 0, 1, 0, 3>; // :874-917  no active bounds
+
 // Calls f.template operator()<Model>() for every registered model; the
 // library, the reference harness and the oracle all dispatch through this
 // one list.
@@ -212,6 +273,9 @@ inline void for_each_model(F&& f)
     f.template operator()<SingleIntegral6>();
     f.template operator()<SingleIntegral7>();
     f.template operator()<SingleIntegral8>();
+    f.template operator()<NestedIntegral1>();
+    f.template operator()<NestedIntegral2>();
+    f.template operator()<NestedIntegral3>();
 }
 
 } // namespace gadfit_b200::models

@@ -155,7 +155,9 @@ int gadfit_ref_create(const char* model_name, RefSolver** out)
 {
     static bool integration_ready { false };
     if (!integration_ready) {
-        gadfit::initIntegration();
+        // Two workspaces: nested integrals need the nesting level stated
+        // (c++/tests/numerical_integration.cpp:226-231)
+        gadfit::initIntegration(gadfit::default_workspace_size, 2);
         integration_ready = true;
     }
     std::unique_ptr<gadfit::LMsolver> solver;

@@ -14,14 +14,15 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c1_fixture.json"
 
 
 def array(src: str, name: str) -> list:
-    m = re.search(r"constexpr std::array %s\s*\{(.*?)\};" % name, src, re.S)
+    m = re.search(r"(?:constexpr std::array|const std::vector<double>) %s\s*\{(.*?)\};" % name, src, re.S)
     return [float(t) for t in m.group(1).replace("\n", " ").split(",") if t.strip()]
 
 
 if __name__ == "__main__":
     src = open(SRC).read()
     names = ["fix_d", "x_data_1", "y_data_1", "x_data_2", "y_data_2",
-             "x_data_single", "y_data_single"]  # fixtures.h:72-154: integration tests
+             "x_data_single", "y_data_single",  # fixtures.h:72-151: integration tests
+             "x_data_double", "y_data_double", "weights_double"]  # fixtures.h:153-237
     out = {n: array(src, n) for n in names}
     out["_source"] = "reference c++/tests/fixtures.h:9-68"
     json.dump(out, open(OUT, "w"))

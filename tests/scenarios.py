@@ -150,6 +150,41 @@ def run_integration(scenario: dict, make_solver, c1_data: dict, n_threads: int =
     return out
 
 
+# The reference's nested double-integral tests, "Double integral (nested)"
+# (c++/tests/numerical_integration.cpp:224-918): 100 points with errors, six
+# parameters (7.0, 1.3, 1.2, 2.0, 0.2, 2.1), acceleration 0.9, fit(0.1).
+# Three of the sixteen sections: all four bounds AD-valued, inner bounds only,
+# no active bounds.  active = activity of p1..p5 (p0 is always active).
+NESTED_SCENARIOS = [
+    dict(name="nested_integral_y1y2x1x2", lines="249-291", active=(1, 1, 1, 1, 1), limit=2,
+         kat=(0.2131810550497416, [15.26735468164642, 1.386383105456653, 0.8486391644471797,
+                                   1.674240469615365, 0.1885677628244937, 1.941800275111635])),
+    dict(name="nested_integral_x1x2", lines="505-547", active=(1, 0, 0, 0, 1), limit=2,
+         kat=(0.0638207048968614, [15.54318299637472, 1.337653916227864, 1.2, 2.0, 0.2,
+                                   2.060422119015556])),
+    dict(name="nested_integral_no_active_bounds", lines="874-917", active=(0, 0, 0, 0, 0), limit=1,
+         kat=(158.6303014282949, [24.35593003546224, 1.3, 1.2, 2.0, 0.2, 2.1])),
+]
+
+
+def run_nested(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1) -> dict:
+    s = make_solver(scenario["name"])
+    x = c1_data["x_data_double"].copy()
+    y = c1_data["y_data_double"].copy()
+    e = c1_data["weights_double"].copy()
+    s._scenario_keep = [x, y, e]
+    s.addDataset(x, y, e)
+    s.setPar(0, 7.0, True)
+    for k, (val, act) in enumerate(zip((1.3, 1.2, 2.0, 0.2, 2.1), scenario["active"]), start=1):
+        s.setPar(k, val, bool(act))
+    s.settings.iteration_limit = scenario["limit"]
+    s.settings.acceleration_threshold = 0.9
+    s.settings.n_threads = n_threads
+    s.fit(0.1)
+    return dict(name=scenario["name"], chi2=s.chi2(), pars=[[s.getParValue(k) for k in range(6)]],
+                trace=s.trace(), iterations=s.iterations(), dof=s.degreesOfFreedom())
+
+
 ALL_SCENARIOS = C1_SCENARIOS + SCALED_SCENARIOS
 
 
