@@ -85,7 +85,7 @@ __device__ __forceinline__ double m_entry(const double* __restrict__ M,
 
 // Sum the partial rows of each data set in slot order (fixed => deterministic)
 // out[s][v] = sum_{slot in [first[s], first[s]+count[s])} partials[slot][v]
-__global__ void k_reduce_slots(const double* __restrict__ partials,
+static __global__ void k_reduce_slots(const double* __restrict__ partials,
                                const int* __restrict__ slot_first,
                                const int* __restrict__ slot_count,
                                const int n_sets,
@@ -110,7 +110,7 @@ __global__ void k_reduce_slots(const double* __restrict__ partials,
 // Column sums over rows in two fixed stages: stage 1, block b sums rows
 // [b*chunk, (b+1)*chunk) for every column; stage 2 (gridDim == 1, chunk ==
 // number of stage-1 blocks) sums the block results.
-__global__ void k_column_sums(const double* __restrict__ in,
+static __global__ void k_column_sums(const double* __restrict__ in,
                               const int n_rows,
                               const int V,
                               const int chunk,
@@ -128,7 +128,7 @@ __global__ void k_column_sums(const double* __restrict__ in,
 }
 
 // Final stage of the chi2 sweep: sum the CTA partials in order
-__global__ void k_sum_partials(const double* __restrict__ partials,
+static __global__ void k_sum_partials(const double* __restrict__ partials,
                                const int n,
                                double* __restrict__ out)
 {
@@ -331,7 +331,7 @@ __global__ void k_local_schur_rhs(const double* __restrict__ v_sets, // [n_sets]
 // bit-identical to a one-thread implementation.
 constexpr int kMaxShared { 32 };
 
-__global__ void __launch_bounds__(32)
+static __global__ void __launch_bounds__(32)
   k_shared_solve(const int pg,
                  const int which,
                  const int update_dtd,
@@ -508,7 +508,7 @@ __global__ void k_acc_ratio_local(const unsigned* __restrict__ active,
 // acc_ratio = sqrt(d2'Dd2 / d1'Dd1) > threshold => delta2 := 0
 // (lm_solver.cpp:394-397).  local_sums = all-reduced [a2, a1] of the local
 // blocks; the shared block is added here.
-__global__ void k_acc_ratio_final(const int pg,
+static __global__ void k_acc_ratio_final(const int pg,
                                   const double threshold,
                                   const double* __restrict__ local_sums,
                                   const double* __restrict__ dtd_global,
@@ -534,7 +534,7 @@ __global__ void k_acc_ratio_final(const int pg,
 
 // saveParameters + updateParameters (lm_solver.cpp:192-204,230-253): beta +=
 // delta1, then (acceleration) beta -= 0.5 * delta2 as a second rounding step.
-__global__ void k_update_parameters(const long long n, // n_sets * NP
+static __global__ void k_update_parameters(const long long n, // n_sets * NP
                                     const int save,
                                     const int accelerate,
                                     const LmState* __restrict__ state,
@@ -559,7 +559,7 @@ __global__ void k_update_parameters(const long long n, // n_sets * NP
 }
 
 // The accept / reject step of lm_solver.cpp:455-494 on the device
-__global__ void k_decide(const int lambda_incs,
+static __global__ void k_decide(const int lambda_incs,
                          const double lambda_down,
                          const double lambda_up,
                          LmState* __restrict__ state,
@@ -590,7 +590,7 @@ __global__ void k_decide(const int lambda_incs,
 
 // revertParameters (lm_solver.cpp:206-218), predicated on the device-side
 // decision so no host round trip sits between k_decide and the revert
-__global__ void k_revert_if_rejected(const long long n,
+static __global__ void k_revert_if_rejected(const long long n,
                                      const LmState* __restrict__ state,
                                      const double* __restrict__ par_old,
                                      double* __restrict__ par)

@@ -274,15 +274,10 @@ struct ModelOpsImpl final : ModelOps
     }
 };
 
-inline auto make_model_ops(const char* model_name) -> std::unique_ptr<ModelOps>
-{
-    std::unique_ptr<ModelOps> ops;
-    models::for_each_model([&]<class Model>() {
-        if (!ops && std::string { model_name } == Model::name) {
-            ops = std::make_unique<ModelOpsImpl<Model>>();
-        }
-    });
-    return ops;
-}
+// One translation unit per model group (model_group.cu compiled with
+// -DGADFIT_MODEL_GROUP=k) defines make_model_ops_group<k>; solver.cu only
+// dispatches, so the kernel instantiations build in parallel.
+template <int GROUP>
+auto make_model_ops_group(const char* model_name) -> std::unique_ptr<ModelOps>;
 
 } // namespace gadfit_b200

@@ -1324,7 +1324,13 @@ int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out)
         return GADFIT_B200_INVALID_ARGUMENT;
     }
     try {
-        auto ops { make_model_ops(model_name) };
+        // kernels of each model group live in their own translation unit
+        std::unique_ptr<ModelOps> ops;
+        static_for<0, models::n_model_groups>([&](auto G) {
+            if (!ops) {
+                ops = make_model_ops_group<G>(model_name);
+            }
+        });
         if (!ops) {
             return GADFIT_B200_UNKNOWN_MODEL;
         }

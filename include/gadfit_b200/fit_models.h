@@ -256,26 +256,46 @@ using NestedIntegral3 = NestedIntegral<2, 0, 1, 0, 3>; // :874-917  no active bo
 
 // Calls f.template operator()<Model>() for every registered model; the
 // library, the reference harness and the oracle all dispatch through this
-// one list.
+// one list.  The GROUP variants exist so that the CUDA library can compile
+// the (template-heavy) groups in separate translation units in parallel.
+template <int GROUP, class F>
+inline void for_each_model_in_group(F&& f)
+{
+    if constexpr (GROUP == 0) { // BASELINE workloads
+        f.template operator()<Exponential>();
+        f.template operator()<GaussHermite3>();
+        f.template operator()<GaussLinearBg>();
+        f.template operator()<ConvExpGauss>();
+        f.template operator()<LorentzDoubleInt>();
+    } else if constexpr (GROUP == 1) { // adaptive single integrals
+        f.template operator()<SingleIntegral1>();
+        f.template operator()<SingleIntegral2>();
+        f.template operator()<SingleIntegral3>();
+        f.template operator()<SingleIntegral4>();
+    } else if constexpr (GROUP == 2) {
+        f.template operator()<SingleIntegral5>();
+        f.template operator()<SingleIntegral6>();
+        f.template operator()<SingleIntegral7>();
+        f.template operator()<SingleIntegral8>();
+    } else if constexpr (GROUP == 3) { // nested adaptive double integrals
+        f.template operator()<NestedIntegral1>();
+    } else if constexpr (GROUP == 4) {
+        f.template operator()<NestedIntegral2>();
+    } else if constexpr (GROUP == 5) {
+        f.template operator()<NestedIntegral3>();
+    }
+}
+constexpr int n_model_groups { 6 };
+
 template <class F>
 inline void for_each_model(F&& f)
 {
-    f.template operator()<Exponential>();
-    f.template operator()<GaussHermite3>();
-    f.template operator()<GaussLinearBg>();
-    f.template operator()<ConvExpGauss>();
-    f.template operator()<LorentzDoubleInt>();
-    f.template operator()<SingleIntegral1>();
-    f.template operator()<SingleIntegral2>();
-    f.template operator()<SingleIntegral3>();
-    f.template operator()<SingleIntegral4>();
-    f.template operator()<SingleIntegral5>();
-    f.template operator()<SingleIntegral6>();
-    f.template operator()<SingleIntegral7>();
-    f.template operator()<SingleIntegral8>();
-    f.template operator()<NestedIntegral1>();
-    f.template operator()<NestedIntegral2>();
-    f.template operator()<NestedIntegral3>();
+    for_each_model_in_group<0>(f);
+    for_each_model_in_group<1>(f);
+    for_each_model_in_group<2>(f);
+    for_each_model_in_group<3>(f);
+    for_each_model_in_group<4>(f);
+    for_each_model_in_group<5>(f);
 }
 
 } // namespace gadfit_b200::models

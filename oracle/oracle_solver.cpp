@@ -70,6 +70,7 @@ struct OracleSolver
     gadfit_b200_settings settings {};
     std::vector<double> DTD_min { 0.0 };
     int mode { 0 }; // 0 auto, 1 dense, 2 block-arrow
+    bool extended { false }; // long double accumulation of the shared block (rounding probe)
 
     // Indices
     long long n_active { 0 };
@@ -225,6 +226,21 @@ struct OracleSolver
     double chi2()
     {
         const double t0 { omp_get_wtime() };
+        if (extended) {
+            long double sum_x { 0.0L };
+            for (size_t s = 0; s < sets.size(); ++s) {
+                const auto& set { sets[s] };
+                const auto& p { pars[s] };
+#pragma omp parallel for reduction(+ : sum_x) num_threads(threads())
+                for (int i = 0; i < set.n; ++i) {
+                    const double diff { (set.y[i] - eval(p, set.x[i])) / set.errors[i] };
+                    sum_x += static_cast<long double>(diff) * diff;
+                }
+            }
+            seconds[1] += omp_get_wtime() - t0;
+            ++calls[1];
+            return static_cast<double>(sum_x);
+        }
         double sum { 0.0 };
         for (size_t s = 0; s < sets.size(); ++s) {
             const auto& set { sets[s] };
@@ -296,6 +312,11 @@ struct OracleSolver
         // structural blocks, and dgemv, lapack_fallback.cpp:43-57
         std::fill(G.begin(), G.end(), 0.0);
         std::fill(right_side.begin(), right_side.end(), 0.0);
+        // Rounding probe (mode bit 4): the shared block and J^T r accumulated
+        // in long double, to tell which of two double-precision summation
+        // orders is closer to the exact sums (tools/full_size_parity.py)
+        std::vector<long double> Gx(extended ? G.size() : 0, 0.0L);
+        std::vector<long double> rx(extended ? static_cast<size_t>(pg) : 0, 0.0L);
         for (int s = 0; s < S; ++s) {
             const auto& cols { column[s] };
             const int ps { static_cast<int>(cols.size()) };
@@ -312,12 +333,21 @@ struct OracleSolver
                 for (size_t a = 0; a < gpos.size(); ++a) {
                     const long long ca { cols[gpos[a]] };
                     for (size_t b = 0; b < gpos.size(); ++b) {
-                        G[ca * pg + cols[gpos[b]]] += row[gpos[a]] * row[gpos[b]];
+                        if (extended) {
+                            Gx[ca * pg + cols[gpos[b]]] +=
+                              static_cast<long double>(row[gpos[a]]) * row[gpos[b]];
+                        } else {
+                            G[ca * pg + cols[gpos[b]]] += row[gpos[a]] * row[gpos[b]];
+                        }
                     }
                     for (int b = 0; b < pl; ++b) {
                         C[s][ca * pl + b] += row[gpos[a]] * row[lpos[b]];
                     }
-                    right_side[ca] += row[gpos[a]] * r;
+                    if (extended) {
+                        rx[ca] += static_cast<long double>(row[gpos[a]]) * r;
+                    } else {
+                        right_side[ca] += row[gpos[a]] * r;
+                    }
                 }
                 for (int a = 0; a < pl; ++a) {
                     for (int b = 0; b < pl; ++b) {
@@ -325,6 +355,14 @@ struct OracleSolver
                     }
                     right_side[cols[lpos[a]]] += row[lpos[a]] * r;
                 }
+            }
+        }
+        if (extended) {
+            for (size_t i = 0; i < G.size(); ++i) {
+                G[i] = static_cast<double>(Gx[i]);
+            }
+            for (int a = 0; a < pg; ++a) {
+                right_side[a] = static_cast<double>(rx[a]);
             }
         }
         // lm_solver.cpp:326-329
@@ -768,10 +806,12 @@ int gadfit_oracle_set_settings(OracleSolver* h, const gadfit_b200_settings* s)
     return GADFIT_B200_OK;
 }
 
-// 0 = automatic (dense for n <= 400), 1 = dense, 2 = block-arrow
+// 0 = automatic (dense for n <= 400), 1 = dense, 2 = block-arrow; +4 = accumulate the
+// shared block, J^T r and chi2 in long double (rounding probe)
 int gadfit_oracle_set_mode(OracleSolver* h, int mode)
 {
-    h->mode = mode;
+    h->mode = mode & 3;
+    h->extended = (mode & 4) != 0;
     return GADFIT_B200_OK;
 }
 
