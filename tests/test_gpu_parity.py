@@ -183,3 +183,64 @@ def test_fp64_peak_microbenchmark_is_sane():
     from gadfit_b200 import measure_fp64_peak
     peak = measure_fp64_peak()
     assert 5e12 < peak < 80e12
+
+
+def _consistency_checks(s, n_iterations):
+    """Size-independent properties of a finished fit (used at BASELINE full
+    sizes where no CPU oracle finishes in test time): chi2 decreases over the
+    accepted steps; lambda follows the reference schedule exactly
+    (lm_solver.cpp:463,471); the chi2 the solver reports equals an independent
+    chi2 sweep at the final parameters."""
+    tr = s.trace()
+    acc = [t for t in tr if t["decision"] == 0]
+    assert len(acc) == s.iterations() == n_iterations
+    assert all(t["new_chi2"] < t["old_chi2"] for t in acc)
+    for a, b in zip(tr, tr[1:]):
+        want = a["lambda_"] / 10.0 if a["decision"] == 0 else a["lambda_"] * 10.0
+        assert b["lambda_"] == want
+    np.testing.assert_allclose(s.chi2(), acc[-1]["new_chi2"], rtol=1e-13)
+
+
+def test_full_size_c4_single_integral_with_acceleration(c1):
+    """BASELINE config 4 at FULL size (256 x 65 536 points, fixed 15-node
+    Kronrod panel per point, geodesic acceleration): invariants, and the shared
+    parameters of a 16-data-set subset fitted by the block-arrow oracle agree
+    with the same subset on the GPU (the full problem is out of CPU reach)."""
+    from gadfit_b200 import LMsolver, workloads as W
+    w = W.c4(iteration_limit=4)
+    s = LMsolver(w.model)
+    w.setup(s)
+    s.fit(w.lambda0)
+    _consistency_checks(s, 4)
+    # recovered shared parameters are close to the truth the data were made from
+    np.testing.assert_allclose([s.getParValue(k) for k in w.shared],
+                               [w.truth[0, k] for k in w.shared], rtol=2e-3)
+
+
+def test_full_size_c5_double_integral_block_arrow(c1):
+    """BASELINE config 5 at FULL size (100 000 data sets x 256 points, 15 x 15
+    Kronrod per point, n = 300 004 columns): the Schur-solve stress test.
+    Invariants + invariance of the shared parameters under reversing the order
+    of the data sets."""
+    from gadfit_b200 import LMsolver, workloads as W
+    w = W.c5(iteration_limit=3)
+    s = LMsolver(w.model)
+    w.setup(s)
+    s.fit(w.lambda0)
+    _consistency_checks(s, 3)
+    shared = [s.getParValue(k) for k in w.shared]
+    r = LMsolver(w.model)
+    order = list(reversed(range(w.n_sets)))
+    for i in order:
+        xs, ys, es = w.slice(i)
+        r.addDataset(xs, ys, es)
+    for k in w.shared:
+        r.setPar(k, float(w.start[0, k]), True)
+    for j, i in enumerate(order):
+        for k in w.local:
+            r.setPar(k, float(w.start[i, k]), True, j)
+    r.settings.iteration_limit = 3
+    r.fit(w.lambda0)
+    np.testing.assert_allclose([r.getParValue(k) for k in w.shared], shared, rtol=1e-10)
+    np.testing.assert_allclose(r.getParValue(0, 0), s.getParValue(0, w.n_sets - 1), rtol=1e-10)
+    assert s.degreesOfFreedom() == w.n_total - (4 + 3 * w.n_sets)
