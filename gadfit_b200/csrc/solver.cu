@@ -723,23 +723,33 @@ struct SolverImpl
         const int VG { shared_len() };
         const bool accelerate { settings.acceleration_threshold > 0.0 };
         t_linalg.start(stream);
-        d_schur_sums.ensure(std::max(VG, 1));
-        if (n_local_sets > 0) {
-            ops->local_schur(stream,
-                             d_M.ptr,
-                             d_active.ptr,
-                             global_mask,
-                             n_local_sets,
-                             d_dtd_local.ptr,
-                             d_state.ptr,
-                             d_factors.ptr,
-                             d_contrib.ptr,
-                             VG);
-            launched();
-        }
-        column_sums(d_contrib.ptr, VG, d_schur_sums.ptr);
-        if (!part.split) {
-            all_reduce(d_schur_sums.ptr, VG);
+        // No data set has a local parameter (n = p_g, e.g. BASELINE config 2):
+        // the Schur complement is empty on every rank, so its kernels and its
+        // all-reduce are skipped and the (zeroed) sums are used as they are
+        const bool has_locals { n_active > pg };
+        if (!has_locals) {
+            if (first_trial) {
+                d_schur_sums.zero(std::max(VG, 1), stream);
+            }
+        } else {
+            d_schur_sums.ensure(std::max(VG, 1));
+            if (n_local_sets > 0) {
+                ops->local_schur(stream,
+                                 d_M.ptr,
+                                 d_active.ptr,
+                                 global_mask,
+                                 n_local_sets,
+                                 d_dtd_local.ptr,
+                                 d_state.ptr,
+                                 d_factors.ptr,
+                                 d_contrib.ptr,
+                                 VG);
+                launched();
+            }
+            column_sums(d_contrib.ptr, VG, d_schur_sums.ptr);
+            if (!part.split) {
+                all_reduce(d_schur_sums.ptr, VG);
+            }
         }
         if (pg > 0) {
             k_shared_solve<<<1, 32, 0, stream>>>(pg,
@@ -1197,6 +1207,31 @@ struct SolverImpl
             }
             return out;
         }
+        case GADFIT_B200_OMEGA: {
+            // The second directional derivative along delta1 at the parameters
+            // of the last Jacobian evaluation (lm_solver.cpp:362-380)
+            const size_t N { static_cast<size_t>(n_datapoints) };
+            if (!have_delta2 || settings.iteration_limit == 0) {
+                throw StatusError { GADFIT_B200_NOT_AVAILABLE,
+                                    "omega exists only with geodesic acceleration" };
+            }
+            DeviceBuffer<double> keep;
+            DeviceBuffer<double> scratch;
+            const size_t n_par { static_cast<size_t>(S) * NP };
+            keep.ensure(n_par);
+            scratch.ensure(static_cast<size_t>(std::max(slots_omega.n_slots, 1)) * NP);
+            d_omega.ensure(N);
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(keep.ptr, d_par.ptr, n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, stream));
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr, d_par_jac.ptr, n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, stream));
+            ops->omega(slots_omega.grid, stream, sweep_args(), d_delta1_par.ptr, d_J.ptr,
+                       n_local_points, slots_omega.base.ptr, scratch.ptr, d_omega.ptr);
+            launched();
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr, keep.ptr, n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, stream));
+            return download(d_omega.ptr, N);
+        }
         case GADFIT_B200_JACOBIAN:
         case GADFIT_B200_RESIDUALS: {
             const size_t N { static_cast<size_t>(n_datapoints) };
@@ -1585,6 +1620,11 @@ int gadfit_b200_set_comm(gadfit_b200_solver* solver,
             throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "bad rank / world size" };
         }
         solver->ensure_device();
+        if (solver->comm != nullptr) {
+            // re-attaching replaces the previous communicator
+            Nccl::instance().commDestroy(solver->comm);
+            solver->comm = nullptr;
+        }
         if (world_size > 1) {
             auto& nccl { Nccl::instance() };
             ncclUniqueId id {};

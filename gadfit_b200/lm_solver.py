@@ -291,6 +291,9 @@ class LMsolver:
     def getDelta2(self):
         return self._array(_capi.DELTA2)
 
+    def getOmega(self):
+        return self._array(_capi.OMEGA)
+
     # -- additions over the reference --------------------------------------
     def trace(self) -> list[dict]:
         """Accept/reject history of the last fit: what the reference prints as

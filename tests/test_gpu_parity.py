@@ -244,3 +244,16 @@ def test_full_size_c5_double_integral_block_arrow(c1):
     np.testing.assert_allclose([r.getParValue(k) for k in w.shared], shared, rtol=1e-10)
     np.testing.assert_allclose(r.getParValue(0, 0), s.getParValue(0, w.n_sets - 1), rtol=1e-10)
     assert s.degreesOfFreedom() == w.n_total - (4 + 3 * w.n_sets)
+
+
+def test_step_vectors_and_omega_with_acceleration(c1):
+    """delta1, delta2 and omega of the last trial step (lm_solver.cpp:348-399)
+    against the oracle, geodesic acceleration on."""
+    sc = [s for s in scenarios.C1_SCENARIOS if s["name"] == "geodesic_acceleration"][0]
+    a, lam, _, _ = scenarios.build(sc, backends.product_solver(), c1)
+    b, _, _, _ = scenarios.build(sc, backends.oracle_solver(1), c1)
+    a.fit(lam)
+    b.fit(lam)
+    np.testing.assert_allclose(a.getDelta1(), b.getDelta1(), rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(a.getDelta2(), b.getDelta2(), rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(a.getOmega(), b._array(9), rtol=1e-9, atol=1e-16)
