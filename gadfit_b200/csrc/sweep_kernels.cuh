@@ -179,8 +179,11 @@ __device__ __forceinline__ double loss_weight(const int loss_type, const double 
 //
 // sum_i ((y_i - f(x_i)) / sigma_i)^2 with passive parameters; the loss
 // function is NOT applied (lm_solver.cpp:521-524).  One partial per CTA.
+#ifndef GADFIT_CHI2_MIN_BLOCKS
+#define GADFIT_CHI2_MIN_BLOCKS 4
+#endif
 template <class Model>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GADFIT_CHI2_MIN_BLOCKS)
   k_chi2(const SweepArgs a, double* __restrict__ block_partials)
 {
     constexpr int NP { Model::n_pars };
