@@ -64,6 +64,44 @@ __global__ void k_dmma(double* out, const int iters, const double a, const doubl
     }
 }
 
+// N independent DMMA accumulator chains in one warp (one warp per SM
+// sub-partition): how much of the pipe can a single warp keep busy?
+template <int N>
+__global__ void k_dmma_chains(double* out, const int iters, const double a, const double b)
+{
+    double acc[N][2];
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        acc[c][0] = threadIdx.x + c;
+        acc[c][1] = c;
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            dmma884(acc[c], a, b);
+        }
+    }
+    double sum { 0.0 };
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        sum += acc[c][0] + acc[c][1];
+    }
+    if (sum == 12345.678) {
+        out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+    }
+}
+
+__global__ void k_dfma_chain(double* out, const int iters, const double a, const double b)
+{
+    double acc { static_cast<double>(threadIdx.x) };
+    for (int i = 0; i < iters; ++i) {
+        acc = ::fma(acc, a, b);
+    }
+    if (acc == 12345.678) {
+        out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    }
+}
+
 // Both in the same warp, interleaved: do the two share one pipe?
 __global__ void k_mixed(double* out, const int iters, const double a, const double b)
 {
@@ -143,6 +181,20 @@ int gadfit_b200_microbench(int which, double* out)
                 k_mixed<<<blocks, threads>>>(sink.ptr, iters, 1.0000001, 1e-9);
                 flops = n_threads / 32.0 * iters * (kChains / 2) * 512.0
                         + n_threads * iters * (kChains / 2) * 8 * 2.0;
+                break;
+            case 3: // DMMA throughput of ONE warp per SM sub-partition with 6 chains
+            case 4: // ... with 1 chain (= issue-to-issue latency of a dependent DMMA)
+            case 5: // DFMA, one warp per sub-partition, 1 chain (latency)
+                if (which == 3) {
+                    k_dmma_chains<6><<<sms, 128>>>(sink.ptr, iters, 1.0000001, 1e-9);
+                    flops = sms * 4.0 * iters * 6 * 512.0;
+                } else if (which == 4) {
+                    k_dmma_chains<1><<<sms, 128>>>(sink.ptr, iters, 1.0000001, 1e-9);
+                    flops = sms * 4.0 * iters * 1 * 512.0;
+                } else {
+                    k_dfma_chain<<<sms, 128>>>(sink.ptr, iters, 1.0000001, 1e-9);
+                    flops = sms * 128.0 * iters * 2.0;
+                }
                 break;
             default:
                 return GADFIT_B200_INVALID_ARGUMENT;
