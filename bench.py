@@ -321,6 +321,7 @@ def main_b200(args, emit):
                          k1_sec=max_over_ranks(k1_sec), k1_calls=k1_calls, tm=solver.timings(),
                          done=solver.iterations()))
     clocks = sampler.stop()
+    comm_stats = solver.commStats() if world > 1 else None
     runs.sort(key=lambda r: r["seconds"])
     med = runs[len(runs) // 2]                      # median repeat
     seconds, launches, k1_sec, k1_calls, tm, done = (med[k] for k in
@@ -421,6 +422,7 @@ def main_b200(args, emit):
             "phase_seconds": {k: v[0] for k, v in tm.items()},
             "phase_calls": {k: v[1] for k, v in tm.items()},
             "gpu_launches": launches,
+            "collectives": comm_stats,
             "clocks": clocks,
             "roofline": roofline,
             "e2e": e2e,

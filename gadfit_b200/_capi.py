@@ -78,7 +78,7 @@ CORE_SYMBOLS = [
 PRODUCT_ONLY_SYMBOLS = [
     "n_models", "model_info", "n_launches", "jacobian_kernel_time",
     "status_name", "set_device", "upload", "comm_unique_id", "set_comm",
-    "partition", "measure_fp64_peak", "microbench",
+    "partition", "measure_fp64_peak", "microbench", "comm_stats",
 ]
 
 
@@ -129,6 +129,7 @@ class Api:
                 "partition": ([C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),
                 "measure_fp64_peak": ([c_double_p], C.c_int),
                 "microbench": ([C.c_int, c_double_p], C.c_int),
+                "comm_stats": ([vp, c_int_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)], C.c_int),
             })
         for name, (argtypes, restype) in sig.items():
             fn = getattr(self.lib, prefix + name)

@@ -8,6 +8,7 @@
 #include <nccl.h> // types and enums only; the functions are resolved with dlsym
 
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -157,6 +158,13 @@ struct Nccl
     CommInitRank commInitRank { nullptr };
     CommDestroy commDestroy { nullptr };
     AllReduce allReduce { nullptr };
+    using AllGather = ncclResult_t (*)(const void*,
+                                       void*,
+                                       size_t,
+                                       ncclDataType_t,
+                                       ncclComm_t,
+                                       cudaStream_t);
+    AllGather allGather { nullptr }; // optional: only the peer-mailbox set-up needs it
     GetErrorString getErrorString { nullptr };
 
     static auto instance() -> Nccl&
@@ -193,6 +201,7 @@ struct Nccl
           reinterpret_cast<CommInitRank>(dlsym(handle, "ncclCommInitRank"));
         commDestroy = reinterpret_cast<CommDestroy>(dlsym(handle, "ncclCommDestroy"));
         allReduce = reinterpret_cast<AllReduce>(dlsym(handle, "ncclAllReduce"));
+        allGather = reinterpret_cast<AllGather>(dlsym(handle, "ncclAllGather"));
         getErrorString =
           reinterpret_cast<GetErrorString>(dlsym(handle, "ncclGetErrorString"));
         if (getUniqueId == nullptr || commInitRank == nullptr

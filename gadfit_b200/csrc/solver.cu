@@ -9,6 +9,7 @@
 // per trial step to know which phase to launch next and to keep the trace.
 
 #include "model_ops.cuh"
+#include "peer_reduce.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -180,6 +181,9 @@ struct SolverImpl
     int rank { 0 };
     int world { 1 };
     ncclComm_t comm { nullptr };
+    PeerReduce peer {};
+    long long n_peer_reductions { 0 };
+    long long n_nccl_reductions { 0 };
 
     // this rank's share of the problem
     Partition part {};
@@ -402,9 +406,19 @@ struct SolverImpl
         if (world <= 1 || n == 0) {
             return;
         }
+        // Small reductions (everything inside the LM loop): one-shot all-reduce
+        // over NVLink peer memory, peer_reduce.cuh.  Large, rare ones (the
+        // point-split M, the final parameter gather): NCCL.
+        if (peer.active && n <= static_cast<size_t>(kPeerMaxDoubles)) {
+            peer.all_reduce(buf, static_cast<int>(n), stream);
+            launched();
+            ++n_peer_reductions;
+            return;
+        }
         auto& nccl { Nccl::instance() };
         nccl.check(nccl.allReduce(buf, buf, n, ncclDouble, ncclSum, comm, stream),
                    "ncclAllReduce");
+        ++n_nccl_reductions;
     }
 
     auto build_slots(SlotTable& table, const int grid) -> void
@@ -1538,6 +1552,18 @@ int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out)
     return guarded(solver, [&] { *out = solver->n_launches; });
 }
 
+int gadfit_b200_comm_stats(gadfit_b200_solver* solver,
+                           int* peer_reduce_active,
+                           long long* n_peer_reductions,
+                           long long* n_nccl_reductions)
+{
+    return guarded(solver, [&] {
+        *peer_reduce_active = solver->peer.active ? 1 : 0;
+        *n_peer_reductions = solver->n_peer_reductions;
+        *n_nccl_reductions = solver->n_nccl_reductions;
+    });
+}
+
 int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
                                      double* seconds_per_launch,
                                      int* launches)
@@ -1631,6 +1657,7 @@ int gadfit_b200_set_comm(gadfit_b200_solver* solver,
             std::memcpy(&id, id_128_bytes, sizeof(id));
             nccl.check(nccl.commInitRank(&solver->comm, world_size, id, rank),
                        "ncclCommInitRank");
+            solver->peer.setup(rank, world_size, solver->comm, solver->stream);
         }
         solver->rank = rank;
         solver->world = world_size;

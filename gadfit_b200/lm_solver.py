@@ -332,6 +332,14 @@ class LMsolver:
                                                    C.byref(n)))
         return sec.value, n.value
 
+    def commStats(self) -> dict:
+        """Multi-GPU: peer-memory all-reduce active? and reduction counts."""
+        active, peer, nccl = C.c_int(), C.c_longlong(), C.c_longlong()
+        self._check(self._api.comm_stats(self._h, C.byref(active), C.byref(peer),
+                                         C.byref(nccl)))
+        return dict(peer_reduce_active=bool(active.value), peer_reductions=peer.value,
+                    nccl_reductions=nccl.value)
+
     def setDevice(self, device: int):
         self._check(self._api.set_device(self._h, int(device)))
 

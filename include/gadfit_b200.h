@@ -188,6 +188,13 @@ GADFIT_B200_API int gadfit_b200_get_timings(gadfit_b200_solver* solver,
                             gadfit_b200_timings* out);
 /* Kernels launched by this solver since creation */
 GADFIT_B200_API int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out);
+/* Multi-GPU: whether the small per-trial reductions run as one-shot
+ * all-reduces over NVLink peer memory (csrc/peer_reduce.cuh) and how many
+ * reductions went that way / through NCCL since creation */
+GADFIT_B200_API int gadfit_b200_comm_stats(gadfit_b200_solver* solver,
+                                           int* peer_reduce_active,
+                                           long long* n_peer_reductions,
+                                           long long* n_nccl_reductions);
 /* Average device time [s] of the Jacobian-sweep kernel alone in the last
  * fit() (CUDA events on the solver's stream) and the number of launches */
 GADFIT_B200_API int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,

@@ -43,7 +43,7 @@ def main():
         got = dict(chi2=s.chi2(), pars=[[s.getParValue(k, j) for k in range(w.n_pars)]
                                         for j in range(w.n_sets)],
                    decisions=[t["decision"] for t in s.trace()], iterations=s.iterations(),
-                   launches=s.launches())
+                   launches=s.launches(), comm=s.commStats())
         if rank == 0:
             o = backends.oracle_solver(2)(w.model)
             w.setup(o)

@@ -31,6 +31,10 @@ def test_two_ranks_reproduce_the_single_process_oracle(tmp_path):
     for name, r in report.items():
         got, want = r["got"], r["want"]
         assert got["launches"] > 0
+        # the per-trial reductions ran over NVLink peer memory, NCCL only for
+        # the large / rare ones (csrc/peer_reduce.cuh)
+        assert got["comm"]["peer_reduce_active"], got["comm"]
+        assert got["comm"]["peer_reductions"] > 0
         n = min(len(got["decisions"]), len(want["decisions"]), 6)
         assert got["decisions"][:n] == want["decisions"][:n], name
         np.testing.assert_allclose(got["chi2"], want["chi2"], rtol=1e-10)
