@@ -295,7 +295,15 @@ def main_b200(args, emit):
     def new_solver(limit):
         return describe(attach(), limit)
 
-    fp64_peak = measure_fp64_peak()
+    # FP64 roofline denominator: DFMA vector loop and DMMA tensor-path loop share
+    # one datapath on B200; the HIGHER of the two measured rates is the peak
+    import ctypes as _C
+    from gadfit_b200._capi import product_api as _api
+    dfma_peak = measure_fp64_peak()
+    _out = _C.c_double()
+    _api().microbench(1, _C.byref(_out))
+    dmma_peak = _out.value
+    fp64_peak = max(dfma_peak, dmma_peak)
 
     # ---- device-resident arm: upload once, warm up, then time K iterations
     solver = new_solver(args.warmup)
@@ -354,19 +362,33 @@ def main_b200(args, emit):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of one k_jacobian launch from the committed `ncu --set full`
+    # capture of this workload (profiles/, written by tools/summarize_profiles.py)
+    traffic = None
+    if args.workload == "C2" and not args.sets and not args.points:
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_summary.json")))
+            traffic = prof["k_jacobian"]["dram_bytes_per_launch"]
+        except (OSError, KeyError, TypeError):
+            traffic = None
     roofline = {
         "bound": "fp64", "kernel": "k_jacobian",
         "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
         "frac": achieved_tflops / (fp64_peak / 1e12) if achieved_tflops else None,
-        "peak_source": "DFMA micro-benchmark measured live on this GPU (gadfit_b200_measure_fp64_peak); "
-                       "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
+        "peak_source": "measured live on this GPU: the higher of a register-resident DFMA loop "
+                       f"({dfma_peak / 1e12:.2f}) and a DMMA m8n8k4 loop ({dmma_peak / 1e12:.2f} TFLOP/s), which "
+                       "share one datapath (csrc/microbench.cu); nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
+        "frac_of_dfma_peak": achieved_tflops / (dfma_peak / 1e12) if achieved_tflops else None,
         "flops_per_point": w.k1_flops_per_point(), "points_per_launch": points_per_gpu,
         "seconds_per_launch": k1_sec, "launches_timed": k1_calls,
         "hbm": {"achieved": bytes_per_launch / k1_sec / 1e9 if k1_sec > 0 else None,
                 "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_per_launch / k1_sec / 1e9 / hbm_peak if k1_sec > 0 else None,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650"},
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": "profiles/r01_summary.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                          "one launch)" if traffic else None,
+        "algorithmic_bytes": bytes_per_launch,
     }
 
     # ---- end-to-end arm: public API from pinned host buffers, H2D inside

@@ -85,6 +85,13 @@ def kernel(tag, name):
     stalls = {h.split("issue_stalled_")[1].split("_per_")[0]: float(vals[i] or 0)
               for i, h in enumerate(hdr) if "smsp__average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio")}
     out["stalls_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:6])
+    # DRAM traffic of this launch in bytes (bench.py reports it as roofline.traffic)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    traffic = 0.0
+    for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        if m in out:
+            traffic += float(out[m]["value"]) * scale.get(out[m]["unit"], 1.0)
+    out["dram_bytes_per_launch"] = traffic
     return out
 
 
