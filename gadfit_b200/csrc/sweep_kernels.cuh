@@ -36,8 +36,24 @@ constexpr int kThreads { 256 };
 #define GADFIT_JAC_MIN_BLOCKS 3
 #endif
 constexpr int kJacobianMinBlocks { GADFIT_JAC_MIN_BLOCKS };
-// Tiles of one data set the chi2 sweep evaluates per loop iteration
-constexpr int kChi2Unroll { 4 };
+// Tiles of one data set the chi2 sweep evaluates per loop iteration: a
+// fitting function may state `static constexpr int chi2_unroll` (cheap
+// closed-form functions profit from 8: instruction-level parallelism across
+// points and shared parameter-only subexpressions; measured on BASELINE
+// config 2: 0.77 / 0.53 / 0.48 ms per sweep for 1 / 4 / 8).  Functions with
+// quadrature loops keep 1 -- their work per point is already long.
+template <class Model, class = void>
+struct Chi2Tuning
+{
+    static constexpr int unroll { 1 };
+    static constexpr int min_blocks { 4 };
+};
+template <class Model>
+struct Chi2Tuning<Model, std::void_t<decltype(Model::chi2_unroll)>>
+{
+    static constexpr int unroll { Model::chi2_unroll };
+    static constexpr int min_blocks { Model::chi2_unroll >= 8 ? 2 : 4 };
+};
 
 struct SweepArgs
 {
@@ -179,14 +195,12 @@ __device__ __forceinline__ double loss_weight(const int loss_type, const double 
 //
 // sum_i ((y_i - f(x_i)) / sigma_i)^2 with passive parameters; the loss
 // function is NOT applied (lm_solver.cpp:521-524).  One partial per CTA.
-#ifndef GADFIT_CHI2_MIN_BLOCKS
-#define GADFIT_CHI2_MIN_BLOCKS 4
-#endif
 template <class Model>
-__global__ void __launch_bounds__(kThreads, GADFIT_CHI2_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
   k_chi2(const SweepArgs a, double* __restrict__ block_partials)
 {
     constexpr int NP { Model::n_pars };
+    constexpr int kChi2Unroll { Chi2Tuning<Model>::unroll };
     __shared__ double s_par[NP];
     __shared__ double s_red[kThreads / 32];
     const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x

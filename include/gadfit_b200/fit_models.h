@@ -27,6 +27,7 @@ struct Exponential
 {
     static constexpr int n_pars { 3 };
     static constexpr const char* name { "exponential" };
+    static constexpr int chi2_unroll { 8 }; // tuning hint, see csrc/sweep_kernels.cuh
     template <class Ctx>
     GADFIT_HD auto operator()(const Ctx& c, const double x) const
     {
@@ -45,6 +46,7 @@ struct GaussHermite3
 {
     static constexpr int n_pars { 20 };
     static constexpr const char* name { "gauss_hermite3" };
+    static constexpr int chi2_unroll { 8 };
 
     template <int K, class Ctx>
     GADFIT_HD static auto peak(const Ctx& c, const double x)
@@ -71,6 +73,7 @@ struct GaussLinearBg
 {
     static constexpr int n_pars { 6 };
     static constexpr const char* name { "gauss_linear_bg" };
+    static constexpr int chi2_unroll { 8 };
     template <class Ctx>
     GADFIT_HD auto operator()(const Ctx& c, const double x) const
     {
