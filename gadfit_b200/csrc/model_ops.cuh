@@ -108,25 +108,26 @@ struct ModelOpsImpl final : ModelOps
         if (device_ready) {
             return;
         }
-        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(Shape::smem_bytes)));
-        GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_jacobian<Model, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(Shape::smem_bytes)));
         // Shared-memory carve-out: the maximum, so that kJacobianMinBlocks CTAs
         // (staging + prefetch buffers each) are resident.  Measured: a smaller
         // carve-out that still fits them (86-90 %, more L1 for the spilled
         // accumulators) changes the sweep time by < 0.1 %.
-        const int carveout { cudaSharedmemCarveoutMaxShared };
-        GADFIT_CUDA_TRY(cudaFuncSetAttribute(
-          k_jacobian<Model, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
-        GADFIT_CUDA_TRY(cudaFuncSetAttribute(
-          k_jacobian<Model, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        const auto configure { [](auto* kernel) {
+            GADFIT_CUDA_TRY(cudaFuncSetAttribute(kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(Shape::smem_bytes)));
+            GADFIT_CUDA_TRY(cudaFuncSetAttribute(kernel,
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared));
+        } };
+        configure(k_jacobian<Model, false, false>);
+        configure(k_jacobian<Model, false, true>);
+        configure(k_jacobian<Model, true, false>);
+        configure(k_jacobian<Model, true, true>);
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model>, kThreads, 0));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &occupancy[1], k_jacobian<Model, true>, kThreads, Shape::smem_bytes));
+          &occupancy[1], k_jacobian<Model, true, false>, kThreads, Shape::smem_bytes));
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[2], k_omega<Model>, kThreads, 0));
         for (int& o : occupancy) {
@@ -161,12 +162,17 @@ struct ModelOpsImpl final : ModelOps
                   double* r_out,
                   const long long n_points) const -> void override
     {
-        if (J_out != nullptr || r_out != nullptr) {
-            k_jacobian<Model, true><<<grid, kThreads, Shape::smem_bytes, st>>>(
+        const bool store { J_out != nullptr || r_out != nullptr };
+        const bool linear { loss == GADFIT_B200_LOSS_LINEAR };
+        const auto launch { [&](auto* kernel) {
+            kernel<<<grid, kThreads, Shape::smem_bytes, st>>>(
               a, loss, slot_base, partials, J_out, r_out, n_points);
+        } };
+        if (store) {
+            linear ? launch(k_jacobian<Model, true, true>) : launch(k_jacobian<Model, true, false>);
         } else {
-            k_jacobian<Model, false><<<grid, kThreads, Shape::smem_bytes, st>>>(
-              a, loss, slot_base, partials, nullptr, nullptr, n_points);
+            linear ? launch(k_jacobian<Model, false, true>)
+                   : launch(k_jacobian<Model, false, false>);
         }
     }
     auto omega(const int grid,

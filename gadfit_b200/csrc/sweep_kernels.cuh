@@ -323,7 +323,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, cons
 // r_out != nullptr so are the weighted residuals.
 // kStore: also write the weighted rows / residuals (J_out, r_out); the plain
 // instantiation carries neither the pointers nor the branches.
-template <class Model, bool kStore>
+template <class Model, bool kStore, bool kLinearLoss>
 __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
   k_jacobian(const SweepArgs a,
              const int loss_type,
@@ -462,8 +462,11 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
             const auto f { Model {}(GradCtx { s_par }, px) };
             // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
             const double res { (py - f.val) * inv_sig };
-            const double w { loss_weight(loss_type, res) };
-            const double scale { w * inv_sig };
+            // Linear loss (the default): the row scale 1/sigma is known before
+            // f is, so tangents can leave the registers as soon as they are
+            // final instead of waiting for the residual
+            const double w { kLinearLoss ? 1.0 : loss_weight(loss_type, res) };
+            const double scale { kLinearLoss ? inv_sig : w * inv_sig };
             double g[NP];
             dense_gradient<NP>(f, g);
 #pragma unroll
