@@ -1208,6 +1208,10 @@ struct SolverImpl
                 || (which == GADFIT_B200_DELTA2 && !have_delta2)) {
                 return out;
             }
+            if (which == GADFIT_B200_DELTA2
+                && download(d_state.ptr, 1).front().use_delta2 == 0) {
+                return out; // ratio test failed: zero-filled, lm_solver.cpp:394-396
+            }
             const auto d { download(which == GADFIT_B200_DELTA1 ? d_delta1_par.ptr
                                                                  : d_delta2_par.ptr,
                                     static_cast<size_t>(S) * NP) };

@@ -19,7 +19,9 @@
 // c.kronrod(...) / c.kronrod2d(...) give the fixed 15-point Kronrod panel of
 // the reference (numerical_integration.cpp:133-148,189-215);
 // c.integrate(lower, upper, f(ctx, t), rel_error) its adaptive G7/K15
-// integrator incl. AD-valued bounds (numerical_integration.cpp:242-423).
+// integrator incl. AD-valued bounds (numerical_integration.cpp:242-423);
+// c.integrate2d(y1, y2, x1, x2, f(ctx, x, y), rel_error) the direct 2-D
+// adaptive integrator (numerical_integration.cpp:426-1146).
 #pragma once
 
 #include "dual.h"
@@ -60,6 +62,17 @@ struct ValueCtx : QuadratureMixin
     {
         return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
     }
+    template <class BY1, class BY2, class BX1, class BX2, class F>
+    GADFIT_HD auto integrate2d(const BY1& y1,
+                               const BY2& y2,
+                               const BX1& x1,
+                               const BX2& x2,
+                               F&& f,
+                               const double rel_error = k_default_rel_error,
+                               const double abs_error = 0.0) const
+    {
+        return gadfit_b200::integrate2d(*this, y1, y2, x1, x2, f, rel_error, abs_error);
+    }
     template <int K>
     GADFIT_HD Passive get() const
     {
@@ -80,6 +93,17 @@ struct GradCtx : QuadratureMixin
                              const double abs_error = 0.0) const
     {
         return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+    }
+    template <class BY1, class BY2, class BX1, class BX2, class F>
+    GADFIT_HD auto integrate2d(const BY1& y1,
+                               const BY2& y2,
+                               const BX1& x1,
+                               const BX2& x2,
+                               F&& f,
+                               const double rel_error = k_default_rel_error,
+                               const double abs_error = 0.0) const
+    {
+        return gadfit_b200::integrate2d(*this, y1, y2, x1, x2, f, rel_error, abs_error);
     }
     template <int K>
     GADFIT_HD SDual<(1U << K)> get() const
@@ -107,6 +131,17 @@ struct Dir2Ctx : QuadratureMixin
                              const double abs_error = 0.0) const
     {
         return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+    }
+    template <class BY1, class BY2, class BX1, class BX2, class F>
+    GADFIT_HD auto integrate2d(const BY1& y1,
+                               const BY2& y2,
+                               const BX1& x1,
+                               const BX2& x2,
+                               F&& f,
+                               const double rel_error = k_default_rel_error,
+                               const double abs_error = 0.0) const
+    {
+        return gadfit_b200::integrate2d(*this, y1, y2, x1, x2, f, rel_error, abs_error);
     }
     template <int K>
     GADFIT_HD Dir2 get() const

@@ -20,6 +20,9 @@
 
 #include "fit_function.h"
 
+#include <tuple>
+#include <utility>
+
 namespace gadfit_b200::models {
 
 // c++/tests/lm_solver.cpp:11-19 (also c++/tests/example.cpp:11-19)
@@ -257,6 +260,116 @@ using NestedIntegral1 = NestedIntegral<0, 0, 1, 0, 1>; // :249-291  y1 y2 x1 x2
 using NestedIntegral2 = NestedIntegral<1, 0, 1, 2, 1>; // :505-547  x1 x2
 using NestedIntegral3 = NestedIntegral<2, 0, 1, 0, 3>; // :874-917  no active bounds
 
+// The reference's direct double-integral test function ("Double integral
+// (direct)", reference c++/tests/numerical_integration.cpp:930-1440): one
+// 2-D adaptive integral over a rectangle whose four edges depend on the
+// fitting parameters [p0 .. p6]:
+//   f(x) = 1/x * int_{y1}^{y2} int_{x1}^{x2} e^{-v} log((e^u - 0.9) q(v) + 1)/u du dv,
+//   q(v) = 1 + p0 p1 erf(v)
+// Bound codes (".val" = the bound enters as a plain number, as in the
+// reference sections that switch individual Leibniz terms off):
+//   y1: 0 = p4 (p1 - p2), 1 = same .val, 2 = (p1 - p2).val
+//   y2: 0 = p3 p6,        1 = same .val, 2 = p3
+//   x1: 0 = p4 p6,        1 = same .val
+//   x2: 0 = p5 / p1,      1 = same .val, 2 = p5.val
+template <int ID, int Y1, int Y2, int X1, int X2>
+struct DirectIntegral
+{
+    static constexpr int n_pars { 7 };
+    static constexpr double tolerance { 1e-4 };
+    static constexpr const char* names[15] {
+        "direct_integral_y1y2x1x2", "direct_integral_y1y2x1", "direct_integral_y1y2x2",
+        "direct_integral_y1x1x2",   "direct_integral_y2x1x2", "direct_integral_y1y2",
+        "direct_integral_x1x2",     "direct_integral_y1x2",   "direct_integral_y2x1",
+        "direct_integral_y1x1",     "direct_integral_y2x2",   "direct_integral_y1",
+        "direct_integral_y2",       "direct_integral_x1",     "direct_integral_x2"
+    };
+    static constexpr const char* name { names[ID] };
+
+    template <class Ctx>
+    GADFIT_HD static auto y1(const Ctx& c)
+    {
+        if constexpr (Y1 == 0) {
+            return par<4>(c) * (par<1>(c) - par<2>(c));
+        } else if constexpr (Y1 == 1) {
+            return (par<4>(c) * (par<1>(c) - par<2>(c))).val;
+        } else {
+            return (par<1>(c) - par<2>(c)).val;
+        }
+    }
+    template <class Ctx>
+    GADFIT_HD static auto y2(const Ctx& c)
+    {
+        if constexpr (Y2 == 0) {
+            return par<3>(c) * par<6>(c);
+        } else if constexpr (Y2 == 1) {
+            return (par<3>(c) * par<6>(c)).val;
+        } else {
+            return par<3>(c);
+        }
+    }
+    template <class Ctx>
+    GADFIT_HD static auto x1(const Ctx& c)
+    {
+        if constexpr (X1 == 0) {
+            return par<4>(c) * par<6>(c);
+        } else {
+            return (par<4>(c) * par<6>(c)).val;
+        }
+    }
+    template <class Ctx>
+    GADFIT_HD static auto x2(const Ctx& c)
+    {
+        if constexpr (X2 == 0) {
+            return par<5>(c) / par<1>(c);
+        } else if constexpr (X2 == 1) {
+            return (par<5>(c) / par<1>(c)).val;
+        } else {
+            return par<5>(c).val;
+        }
+    }
+
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto integrand { [](const auto& cc, const auto& u, const auto& v) {
+            const auto q { 1 + par<0>(cc) * par<1>(cc) * erf(v) };
+            return exp(-v) * log((exp(u) - 0.9) * q + 1.0) / u;
+        } };
+        return c.integrate2d(y1(c), y2(c), x1(c), x2(c), integrand, tolerance) / x;
+    }
+};
+using DirectIntegral1 = DirectIntegral<0, 0, 0, 0, 0>;   // :951-971 and :1409-1440
+using DirectIntegral2 = DirectIntegral<1, 0, 0, 0, 1>;   // :972-1002
+using DirectIntegral3 = DirectIntegral<2, 0, 0, 1, 0>;   // :1003-1033
+using DirectIntegral4 = DirectIntegral<3, 0, 1, 0, 0>;   // :1034-1064
+using DirectIntegral5 = DirectIntegral<4, 1, 0, 0, 0>;   // :1065-1095
+using DirectIntegral6 = DirectIntegral<5, 0, 0, 1, 2>;   // :1096-1126
+using DirectIntegral7 = DirectIntegral<6, 2, 1, 0, 0>;   // :1127-1157
+using DirectIntegral8 = DirectIntegral<7, 0, 1, 1, 0>;   // :1158-1188
+using DirectIntegral9 = DirectIntegral<8, 1, 2, 0, 1>;   // :1189-1219
+using DirectIntegral10 = DirectIntegral<9, 0, 1, 0, 1>;  // :1220-1250
+using DirectIntegral11 = DirectIntegral<10, 1, 0, 1, 0>; // :1251-1281
+using DirectIntegral12 = DirectIntegral<11, 0, 1, 1, 2>; // :1282-1312
+using DirectIntegral13 = DirectIntegral<12, 1, 0, 1, 1>; // :1313-1344
+using DirectIntegral14 = DirectIntegral<13, 2, 1, 0, 1>; // :1345-1376
+using DirectIntegral15 = DirectIntegral<14, 1, 1, 1, 0>; // :1377-1408
+using DirectIntegrals = std::tuple<DirectIntegral1,
+                                   DirectIntegral2,
+                                   DirectIntegral3,
+                                   DirectIntegral4,
+                                   DirectIntegral5,
+                                   DirectIntegral6,
+                                   DirectIntegral7,
+                                   DirectIntegral8,
+                                   DirectIntegral9,
+                                   DirectIntegral10,
+                                   DirectIntegral11,
+                                   DirectIntegral12,
+                                   DirectIntegral13,
+                                   DirectIntegral14,
+                                   DirectIntegral15>;
+
 // Calls f.template operator()<Model>() for every registered model; the
 // library, the reference harness and the oracle all dispatch through this
 // one list.  The GROUP variants exist so that the CUDA library can compile
@@ -286,19 +399,21 @@ inline void for_each_model_in_group(F&& f)
         f.template operator()<NestedIntegral2>();
     } else if constexpr (GROUP == 5) {
         f.template operator()<NestedIntegral3>();
+    } else { // direct adaptive double integrals, one per group
+        f.template operator()<std::tuple_element_t<GROUP - 6, DirectIntegrals>>();
     }
 }
-constexpr int n_model_groups { 6 };
+constexpr int n_model_groups { 6 + static_cast<int>(std::tuple_size_v<DirectIntegrals>) };
 
+template <class F, int... GROUPS>
+inline void for_each_model_impl(F&& f, std::integer_sequence<int, GROUPS...>)
+{
+    (for_each_model_in_group<GROUPS>(f), ...);
+}
 template <class F>
 inline void for_each_model(F&& f)
 {
-    for_each_model_in_group<0>(f);
-    for_each_model_in_group<1>(f);
-    for_each_model_in_group<2>(f);
-    for_each_model_in_group<3>(f);
-    for_each_model_in_group<4>(f);
-    for_each_model_in_group<5>(f);
+    for_each_model_impl(f, std::make_integer_sequence<int, n_model_groups> {});
 }
 
 } // namespace gadfit_b200::models

@@ -287,4 +287,192 @@ GADFIT_HD auto integrate(const Ctx& c,
     return leibniz(c, f, leibniz(c, f, result, lower_bound, -1.0), upper_bound, 1.0);
 }
 
+// ===========================================================================
+// Adaptive Gauss-Kronrod integration, direct 2-D
+// ===========================================================================
+//
+// Counterpart of the 2-D gadfit::integrate() (reference
+// numerical_integration.cpp:426-526): 15 x 15 Kronrod / 7 x 7 Gauss on a
+// rectangle, bisect the rectangle with the largest error estimate along its
+// (relatively) longer side, final pass with AD on; AD-valued bounds add the
+// Leibniz terms of traceRecordY1/Y2/X1/X2 (:533-811), which are 1-D adaptive
+// integrals along the moving edge.  The integrand is f(ctx, x, y); y is the
+// outer variable (bounds y1, y2), x the inner one (bounds x1, x2).
+
+constexpr int k_max_panels_2d { 64 };
+
+// numerical_integration.cpp:150-187
+template <class Ctx, class F>
+GADFIT_HD double gauss_kronrod2d(const Ctx& passive_ctx,
+                                 F&& f,
+                                 const double y1,
+                                 const double y2,
+                                 const double x1,
+                                 const double x2,
+                                 double& abs_error)
+{
+    const double outer_scale { (y2 - y1) / 2 };
+    const double outer_shift { (y1 + y2) / 2 };
+    const double inner_scale { (x2 - x1) / 2 };
+    const double inner_shift { (x1 + x2) / 2 };
+    double sum_kronrod { 0.0 };
+    double sum_gauss { 0.0 };
+#pragma unroll 1
+    for (int i = 0; i < k15_size; ++i) {
+        const double arg_x { inner_scale * k15_root(i) + inner_shift };
+#pragma unroll 1
+        for (int j = 0; j < k15_size; ++j) {
+            const double arg_y { outer_scale * k15_root(j) + outer_shift };
+            const double val { value_of(f(passive_ctx, Passive { arg_x }, Passive { arg_y })) };
+            sum_kronrod += (k15_weight(i) * k15_weight(j)) * val;
+            if (i % 2 == 1 && j % 2 == 1) {
+                sum_gauss += (g7_weight(i / 2) * g7_weight(j / 2)) * val;
+            }
+        }
+    }
+    sum_kronrod *= outer_scale * inner_scale;
+    abs_error = ::fabs(sum_kronrod - outer_scale * inner_scale * sum_gauss);
+    return sum_kronrod;
+}
+
+// Leibniz term of one AD-valued bound of the rectangle.  AXIS 0: `bound` is a
+// y bound (the edge integral runs over x in [o1, o2]); AXIS 1: an x bound (the
+// edge integral runs over y).  sign = +1 upper, -1 lower.
+template <int AXIS, class Ctx, class F, class R, class B, class O1, class O2>
+GADFIT_HD auto leibniz2d(const Ctx& c,
+                         F&& f,
+                         const R& result,
+                         const B& bound,
+                         const O1& o1,
+                         const O2& o2,
+                         const double sign,
+                         const double rel_error,
+                         const double abs_error)
+{
+    if constexpr (is_passive_bound<B>::value) {
+        return result;
+    } else {
+        const double lo { bound_value(o1) };
+        const double hi { bound_value(o2) };
+        // f along the edge; `edge` is the fixed coordinate (passive or active)
+        const auto along { [&f](const auto& cc, const auto& t, const auto& edge) {
+            if constexpr (AXIS == 0) {
+                return f(cc, t, edge);
+            } else {
+                return f(cc, edge, t);
+            }
+        } };
+        const Passive b_passive { bound.val };
+        const auto pc { c.passive() };
+        const double edge_integral { value_of(integrate(
+          pc, lo, hi, [&](const auto& cc, const auto& t) { return along(cc, t, b_passive); },
+          rel_error, abs_error)) };
+        if constexpr (std::is_same_v<B, Dir2>) {
+            // numerical_integration.cpp:561-590 (and the three siblings)
+            const double f_hi { value_of(along(pc, Passive { hi }, b_passive)) };
+            const double f_lo { value_of(along(pc, Passive { lo }, b_passive)) };
+            const auto f_chi { integrate(
+              c, lo, hi, [&](const auto& cc, const auto& t) { return along(cc, t, b_passive); },
+              rel_error, abs_error) };
+            const auto f_full { integrate(
+              c, lo, hi, [&](const auto& cc, const auto& t) { return along(cc, t, bound); },
+              rel_error, abs_error) };
+            Dir2 r { as_dir2(result) };
+            r.d += sign * bound.d * edge_integral;
+            r.dd += sign
+                    * (bound.dd * edge_integral
+                       + bound.d * (d_of(o2) * f_hi - d_of(o1) * f_lo + d_of(f_chi) + d_of(f_full)));
+            return r;
+        } else {
+            return result + (bound - bound.val) * (sign * edge_integral);
+        }
+    }
+}
+
+template <class Ctx, class F, class BY1, class BY2, class BX1, class BX2>
+GADFIT_HD auto integrate2d(const Ctx& c,
+                           const BY1& y1_bound,
+                           const BY2& y2_bound,
+                           const BX1& x1_bound,
+                           const BX2& x2_bound,
+                           F&& f,
+                           const double rel_error = k_default_rel_error,
+                           const double abs_error = 0.0)
+{
+    const double y1 { bound_value(y1_bound) };
+    const double y2 { bound_value(y2_bound) };
+    const double x1 { bound_value(x1_bound) };
+    const double x2 { bound_value(x2_bound) };
+    const auto pc { c.passive() };
+    const double y_scale_inv { 1.0 / (y2 - y1) };
+    const double x_scale_inv { 1.0 / (x2 - x1) };
+    double by1[k_max_panels_2d];
+    double by2[k_max_panels_2d];
+    double bx1[k_max_panels_2d];
+    double bx2[k_max_panels_2d];
+    double sums[k_max_panels_2d];
+    double errs[k_max_panels_2d];
+    by1[0] = y1;
+    by2[0] = y2;
+    bx1[0] = x1;
+    bx2[0] = x2;
+    sums[0] = gauss_kronrod2d(pc, f, y1, y2, x1, x2, errs[0]);
+    int n_panels { 0 };
+    for (int iter = 0; iter + 1 < k_max_panels_2d; ++iter) {
+        const int next { iter + 1 };
+        int worst { 0 };
+        for (int i = 1; i <= iter; ++i) {
+            if (errs[worst] < errs[i]) {
+                worst = i;
+            }
+        }
+        const double cy1 { by1[worst] };
+        const double cy2 { by2[worst] };
+        const double cx1 { bx1[worst] };
+        const double cx2 { bx2[worst] };
+        if (y_scale_inv * (cy2 - cy1) > x_scale_inv * (cx2 - cx1)) {
+            const double middle { (cy1 + cy2) / 2 };
+            sums[worst] = gauss_kronrod2d(pc, f, cy1, middle, cx1, cx2, errs[worst]);
+            sums[next] = gauss_kronrod2d(pc, f, middle, cy2, cx1, cx2, errs[next]);
+            by2[worst] = middle;
+            by1[next] = middle;
+            by2[next] = cy2;
+            bx1[next] = cx1;
+            bx2[next] = cx2;
+        } else {
+            const double middle { (cx1 + cx2) / 2 };
+            sums[worst] = gauss_kronrod2d(pc, f, cy1, cy2, cx1, middle, errs[worst]);
+            sums[next] = gauss_kronrod2d(pc, f, cy1, cy2, middle, cx2, errs[next]);
+            bx2[worst] = middle;
+            by1[next] = cy1;
+            by2[next] = cy2;
+            bx1[next] = middle;
+            bx2[next] = cx2;
+        }
+        double errors_sum { 0.0 };
+        double sums_sum { 0.0 };
+        for (int i = 0; i < iter + 2; ++i) {
+            errors_sum += errs[i];
+            sums_sum += sums[i];
+        }
+        if (errors_sum < abs_error || errors_sum / sums_sum < rel_error) {
+            n_panels = iter + 2;
+            break;
+        }
+    }
+    const auto active { [&](const Passive& x, const Passive& y) { return f(c, x, y); } };
+    auto result { Passive { 0.0 } + kronrod2d(by1[0], by2[0], bx1[0], bx2[0], active) };
+    for (int i = 1; i < n_panels; ++i) {
+        result = result + kronrod2d(by1[i], by2[i], bx1[i], bx2[i], active);
+    }
+    if (n_panels == 0) {
+        result = result * (0.0 / 0.0); // workspace exhausted => rejected step
+    }
+    // traceRecordY1, Y2, X1, X2 in the reference's order (:1131-1144)
+    auto r1 { leibniz2d<0>(c, f, result, y1_bound, x1_bound, x2_bound, -1.0, rel_error, abs_error) };
+    auto r2 { leibniz2d<0>(c, f, r1, y2_bound, x1_bound, x2_bound, 1.0, rel_error, abs_error) };
+    auto r3 { leibniz2d<1>(c, f, r2, x1_bound, y1_bound, y2_bound, -1.0, rel_error, abs_error) };
+    return leibniz2d<1>(c, f, r3, x2_bound, y1_bound, y2_bound, 1.0, rel_error, abs_error);
+}
+
 } // namespace gadfit_b200

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <numbers>
 #include <type_traits>
+#include <vector>
 
 namespace gadfit_oracle {
 
@@ -454,6 +455,159 @@ struct Ctx
         FVar result { integrate(lower.val, upper.val, f, rel, abs) };
         bound_term(f, lower, -1.0, result);
         bound_term(f, upper, 1.0, result);
+        return result;
+    }
+    // Direct 2-D adaptive integration, numerical_integration.cpp:426-526, with
+    // the forward-mode terms of traceRecordY1/Y2/X1/X2 (:533-811) for AD-valued
+    // bounds.  f(ctx, x, y); y1, y2 bound the outer variable, x1, x2 the inner.
+    static auto as_var(const double b) -> FVar { return passive(b); }
+    static auto as_var(const FVar& b) -> FVar { return b; }
+    // G7xG7 / K15xK15 on one rectangle, :150-187
+    template <class F>
+    static auto gaussKronrod2d(F&& fp,
+                               const double y1,
+                               const double y2,
+                               const double x1,
+                               const double x2,
+                               double& abs_error) -> double
+    {
+        const double outer_scale { (y2 - y1) / 2 };
+        const double outer_shift { (y1 + y2) / 2 };
+        const double inner_scale { (x2 - x1) / 2 };
+        const double inner_shift { (x1 + x2) / 2 };
+        double sum_kronrod {};
+        double sum_gauss {};
+        for (int i = 0; i < 15; ++i) {
+            const FVar arg_x { passive(inner_scale * k15_roots[i] + inner_shift) };
+            for (int j = 0; j < 15; ++j) {
+                const FVar arg_y { passive(outer_scale * k15_roots[j] + outer_shift) };
+                const double val { fp(arg_x, arg_y).val };
+                sum_kronrod += (k15_weights[i] * k15_weights[j]) * val;
+                if (i % 2 == 1 && j % 2 == 1) {
+                    sum_gauss += (g7_weights[i / 2] * g7_weights[j / 2]) * val;
+                }
+            }
+        }
+        sum_kronrod *= outer_scale * inner_scale;
+        abs_error = std::abs(sum_kronrod - outer_scale * inner_scale * sum_gauss);
+        return sum_kronrod;
+    }
+    // One moving edge.  y_edge: `bound` is y1 or y2 and the edge integral runs
+    // over x in [o1, o2]; otherwise `bound` is x1 or x2 and it runs over y.
+    template <class F>
+    auto edge_term(F&& f,
+                   const bool y_edge,
+                   const FVar& bound,
+                   const FVar& o1,
+                   const FVar& o2,
+                   const double sign,
+                   const double rel,
+                   const double abs,
+                   FVar& result) const -> void
+    {
+        if (!bound.on) {
+            return;
+        }
+        FVar inactive[64];
+        for (int i = 0; i < n_pars; ++i) {
+            inactive[i] = passive(pars[i].val);
+        }
+        const Ctx pc { inactive, n_pars };
+        const auto along { [&](const Ctx& cc, const FVar& t, const FVar& edge) {
+            return y_edge ? f(cc, t, edge) : f(cc, edge, t);
+        } };
+        const FVar b_passive { passive(bound.val) };
+        const auto fixed { [&](const Ctx& cc, const FVar& t) { return along(cc, t, b_passive); } };
+        const auto fixed_active { [&](const Ctx& cc, const FVar& t) { return along(cc, t, bound); } };
+        const double edge_integral { pc.integrate(o1.val, o2.val, fixed, rel, abs).val };
+        const double f_hi { along(pc, passive(o2.val), b_passive).val };
+        const double f_lo { along(pc, passive(o1.val), b_passive).val };
+        const FVar f_chi { integrate(o1.val, o2.val, fixed, rel, abs) };
+        const FVar f_full { integrate(o1.val, o2.val, fixed_active, rel, abs) };
+        result.d += sign * bound.d * edge_integral;
+        result.dd += sign
+                     * (bound.dd * edge_integral
+                        + bound.d * (o2.d * f_hi - o1.d * f_lo + f_chi.d + f_full.d));
+        result.on = true;
+    }
+    template <class BY1, class BY2, class BX1, class BX2, class F>
+    auto integrate2d(const BY1& y1_bound,
+                     const BY2& y2_bound,
+                     const BX1& x1_bound,
+                     const BX2& x2_bound,
+                     F&& f,
+                     const double rel_error = 2.220446049250313e-14,
+                     const double abs_error = 0.0) const -> FVar
+    {
+        const FVar by1 { as_var(y1_bound) };
+        const FVar by2 { as_var(y2_bound) };
+        const FVar bx1 { as_var(x1_bound) };
+        const FVar bx2 { as_var(x2_bound) };
+        FVar inactive[64];
+        for (int i = 0; i < n_pars; ++i) {
+            inactive[i] = passive(pars[i].val);
+        }
+        const Ctx pc { inactive, n_pars };
+        const auto fp { [&](const FVar& x, const FVar& y) { return f(pc, x, y); } };
+        struct Rect
+        {
+            double y1, y2, x1, x2;
+        };
+        constexpr int workspace { 1000 };
+        std::vector<Rect> rect(workspace + 1);
+        std::vector<double> sums(workspace + 1);
+        std::vector<double> errs(workspace + 1);
+        const double y_scale_inv { 1.0 / (by2.val - by1.val) };
+        const double x_scale_inv { 1.0 / (bx2.val - bx1.val) };
+        rect[0] = { by1.val, by2.val, bx1.val, bx2.val };
+        sums[0] = gaussKronrod2d(fp, by1.val, by2.val, bx1.val, bx2.val, errs[0]);
+        FVar result { passive(std::nan("")) };
+        for (int iter = 0; iter < workspace; ++iter) {
+            const int next { iter + 1 };
+            int worst { 0 };
+            for (int i = 1; i <= iter; ++i) {
+                if (errs[worst] < errs[i]) {
+                    worst = i;
+                }
+            }
+            const Rect cur { rect[worst] };
+            if (y_scale_inv * (cur.y2 - cur.y1) > x_scale_inv * (cur.x2 - cur.x1)) {
+                const double middle { (cur.y1 + cur.y2) / 2 };
+                sums[worst] = gaussKronrod2d(fp, cur.y1, middle, cur.x1, cur.x2, errs[worst]);
+                sums[next] = gaussKronrod2d(fp, middle, cur.y2, cur.x1, cur.x2, errs[next]);
+                rect[worst].y2 = middle;
+                rect[next] = { middle, cur.y2, cur.x1, cur.x2 };
+            } else {
+                const double middle { (cur.x1 + cur.x2) / 2 };
+                sums[worst] = gaussKronrod2d(fp, cur.y1, cur.y2, cur.x1, middle, errs[worst]);
+                sums[next] = gaussKronrod2d(fp, cur.y1, cur.y2, middle, cur.x2, errs[next]);
+                rect[worst].x2 = middle;
+                rect[next] = { cur.y1, cur.y2, middle, cur.x2 };
+            }
+            double errors_sum {};
+            double sums_sum {};
+            for (int i = 0; i < iter + 2; ++i) {
+                errors_sum += errs[i];
+                sums_sum += sums[i];
+            }
+            if (errors_sum < abs_error || errors_sum / sums_sum < rel_error) {
+                result = passive(0.0);
+                for (int i = 0; i < iter + 2; ++i) {
+                    result = result
+                             + gadfit_oracle::kronrod2d(
+                               rect[i].y1,
+                               rect[i].y2,
+                               rect[i].x1,
+                               rect[i].x2,
+                               [&](const FVar& x, const FVar& y) { return f(*this, x, y); });
+                }
+                break;
+            }
+        }
+        edge_term(f, true, by1, bx1, bx2, -1.0, rel_error, abs_error, result);
+        edge_term(f, true, by2, bx1, bx2, 1.0, rel_error, abs_error, result);
+        edge_term(f, false, bx1, by1, by2, -1.0, rel_error, abs_error, result);
+        edge_term(f, false, bx2, by1, by2, 1.0, rel_error, abs_error, result);
         return result;
     }
     template <class F>

@@ -74,6 +74,31 @@ struct RefCtx
           rel_error,
           abs_error);
     }
+    // direct 2-D gadfit::integrate, numerical_integration.h:116-260 (every
+    // combination of double and AdVar bounds)
+    template <class BY1, class BY2, class BX1, class BX2, class F>
+    auto integrate2d(const BY1& y1,
+                     const BY2& y2,
+                     const BX1& x1,
+                     const BX2& x2,
+                     F&& f,
+                     const double rel_error = gadfit::default_rel_error,
+                     const double abs_error = 0.0) const -> gadfit::AdVar
+    {
+        return gadfit::integrate(
+          [&f](const std::vector<gadfit::AdVar>& p,
+               const gadfit::AdVar& x,
+               const gadfit::AdVar& y) {
+              return gadfit::AdVar { f(RefCtx { p }, x, y) };
+          },
+          pars,
+          y1,
+          y2,
+          x1,
+          x2,
+          rel_error,
+          abs_error);
+    }
     template <class F>
     auto kronrod2d(const double outer_lower,
                    const double outer_upper,

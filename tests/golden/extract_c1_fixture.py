@@ -22,7 +22,8 @@ if __name__ == "__main__":
     src = open(SRC).read()
     names = ["fix_d", "x_data_1", "y_data_1", "x_data_2", "y_data_2",
              "x_data_single", "y_data_single",  # fixtures.h:72-151: integration tests
-             "x_data_double", "y_data_double", "weights_double"]  # fixtures.h:153-237
+             "x_data_double", "y_data_double", "weights_double",  # fixtures.h:153-237
+             "y_data_double_direct"]  # fixtures.h:239-265
     out = {n: array(src, n) for n in names}
     out["_source"] = "reference c++/tests/fixtures.h:9-68"
     json.dump(out, open(OUT, "w"))

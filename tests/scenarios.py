@@ -185,6 +185,69 @@ def run_nested(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1) -
                 trace=s.trace(), iterations=s.iterations(), dof=s.degreesOfFreedom())
 
 
+# The reference's direct double-integral tests, "Double integral (direct)"
+# (c++/tests/numerical_integration.cpp:930-1440): 100 points without errors,
+# seven parameters (7.0, 1.3, 1.2, 2.0, 0.2, 2.1, 1.0), iteration limit 2,
+# acceleration 0.9, fit(0.1).  All sixteen sections; `active` = activity of
+# p0..p6, kat = (chi2 to 1e-9 absolute, parameters to 1e-7 relative).
+DIRECT_SCENARIOS = [
+    dict(name="direct_integral_y1y2x1x2", section="Active bounds: y1 y2 x1 x2", lines="951", active=(0, 0, 1, 1, 1, 1, 1),
+         kat=(1.654886495874691e-06, [7, 1.3, 2.066882698115843, 2.462337242876448, 0.1286061153388938, 2.370219247402999, 1.537928956329218])),
+    dict(name="direct_integral_y1y2x1", section="Active bounds: y1 y2 x1", lines="972", active=(1, 0, 0, 1, 1, 0, 0),
+         kat=(4.790523057594158e-09, [9.175204980541729, 1.3, 1.2, 2.516290186341045, 0.1241748448388979, 2.1, 1.0])),
+    dict(name="direct_integral_y1y2x2", section="Active bounds: y1 y2 x2", lines="1003", active=(1, 1, 0, 1, 0, 1, 0),
+         kat=(8.068219436506581e-09, [8.65075393701988, 1.127842104542012, 1.2, 2.391312159920373, 0.2, 2.307754246034183, 1.0])),
+    dict(name="direct_integral_y1x1x2", section="Active bounds: y1 x1 x2", lines="1034", active=(1, 1, 0, 0, 1, 1, 0),
+         kat=(7.949911068776061e-09, [8.623217421789654, 1.12999180500759, 1.2, 2.0, 0.143292615316067, 2.304776775635509, 1.0])),
+    dict(name="direct_integral_y2x1x2", section="Active bounds: y2 x1 x2", lines="1065", active=(1, 0, 0, 1, 0, 1, 1),
+         kat=(0.000213350703610027, [9.671381032914667, 1.3, 1.2, 2.471195537765232, 0.2, 2.436352543805309, 1.282878741340198])),
+    dict(name="direct_integral_y1y2", section="Active bounds: y1 y2", lines="1096", active=(1, 1, 0, 1, 0, 0, 0),
+         kat=(6.66506150605225e-09, [7.666430772544548, 1.520366990688495, 1.2, 2.149840327725317, 0.2, 2.1, 1.0])),
+    dict(name="direct_integral_x1x2", section="Active bounds: x1 x2", lines="1127", active=(1, 0, 0, 0, 1, 1, 0),
+         kat=(1.05553491668674e-08, [9.456196153046807, 1.3, 1.2, 2.0, 0.1108266934567069, 2.419211642876849, 1.0])),
+    dict(name="direct_integral_y1x2", section="Active bounds: y1 x2", lines="1158", active=(1, 1, 0, 0, 0, 1, 0),
+         kat=(1.837877829573166e-08, [9.13367142357661, 1.077434702465759, 1.2, 2.0, 0.2, 2.369246887944458, 1.0])),
+    dict(name="direct_integral_y2x1", section="Active bounds: y2 x1", lines="1189", active=(1, 0, 0, 1, 0, 0, 1),
+         kat=(3.85575335670611e-09, [9.161296077178266, 1.3, 1.2, 2.513226918313678, 0.2, 2.1, 0.6086751941736143])),
+    dict(name="direct_integral_y1x1", section="Active bounds: y1 x1", lines="1220", active=(1, 0, 0, 0, 1, 0, 0),
+         kat=(4.556742521509683e-09, [9.972875346712668, 1.3, 1.2, 2.0, 0.09633003605472064, 2.1, 1.0])),
+    dict(name="direct_integral_y2x2", section="Active bounds: y2 x2", lines="1251", active=(1, 0, 0, 1, 0, 1, 0),
+         kat=(5.373563892617068e-08, [9.405485170085401, 1.3, 1.2, 2.5661598112606, 0.2, 2.403368518336621, 1.0])),
+    dict(name="direct_integral_y1", section="Active bounds: y1", lines="1282", active=(1, 1, 0, 0, 0, 0, 0),
+         kat=(1.443756776956618e-07, [8.13832625826087, 1.657624293024702, 1.2, 2.0, 0.2, 2.1, 1.0])),
+    dict(name="direct_integral_y2", section="Active bounds: y2", lines="1313", active=(0, 0, 0, 1, 0, 0, 0),
+         kat=(0.3053680170120716, [7, 1.3, 1.2, 6.663707134981233, 0.2, 2.1, 1.0])),
+    dict(name="direct_integral_x1", section="Active bounds: x1", lines="1345", active=(0, 0, 0, 0, 1, 0, 0),
+         kat=(7.119221262116694e-07, [7, 1.3, 1.2, 2.0, 0.02430156976447609, 2.1, 1.0])),
+    dict(name="direct_integral_x2", section="Active bounds: x2", lines="1377", active=(0, 0, 0, 0, 0, 1, 0),
+         kat=(2.851428619095947e-06, [7, 1.3, 1.2, 2.0, 0.2, 3.034543683583202, 1.0])),
+    dict(name="direct_integral_y1y2x1x2", section="No active bounds", lines="1409", active=(1, 0, 0, 0, 0, 0, 0),
+         kat=(4.090863893678671e-05, [16.70423680614829, 1.3, 1.2, 2.0, 0.2, 2.1, 1.0])),
+]
+for _s in DIRECT_SCENARIOS:
+    _s["id"] = "direct:" + _s["section"].replace("Active bounds: ", "").replace(" ", "")
+
+
+def run_direct(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1, limit: int = 2,
+               keep: bool = False) -> dict:
+    s = make_solver(scenario["name"])
+    x = c1_data["x_data_double"].copy()
+    y = c1_data["y_data_double_direct"].copy()
+    s._scenario_keep = [x, y]
+    s.addDataset(x, y)
+    for k, (val, act) in enumerate(zip((7.0, 1.3, 1.2, 2.0, 0.2, 2.1, 1.0), scenario["active"])):
+        s.setPar(k, val, bool(act))
+    s.settings.iteration_limit = limit
+    s.settings.acceleration_threshold = 0.9
+    s.settings.n_threads = n_threads
+    s.fit(0.1)
+    rec = dict(name=scenario["id"], chi2=s.chi2(), pars=[[s.getParValue(k) for k in range(7)]],
+               trace=s.trace(), iterations=s.iterations(), dof=s.degreesOfFreedom())
+    if keep:
+        rec["solver"] = s
+    return rec
+
+
 ALL_SCENARIOS = C1_SCENARIOS + SCALED_SCENARIOS
 
 
