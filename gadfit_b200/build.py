@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libgadfit_b200.so")
-N_MODEL_GROUPS = 21  # models::n_model_groups in include/gadfit_b200/fit_models.h
+N_MODEL_GROUPS = 30  # models::n_model_groups in include/gadfit_b200/fit_models.h
 
 NVCC_FLAGS = [
     "-std=c++20", "-O3", "-lineinfo",

@@ -153,18 +153,45 @@ def run_integration(scenario: dict, make_solver, c1_data: dict, n_threads: int =
 # The reference's nested double-integral tests, "Double integral (nested)"
 # (c++/tests/numerical_integration.cpp:224-918): 100 points with errors, six
 # parameters (7.0, 1.3, 1.2, 2.0, 0.2, 2.1), acceleration 0.9, fit(0.1).
-# Three of the sixteen sections: all four bounds AD-valued, inner bounds only,
-# no active bounds.  active = activity of p1..p5 (p0 is always active).
+# All sixteen sections (twelve distinct functors: sections that differ only in
+# which parameters are active share one).  active = activity of p1..p5 (p0 is
+# always active); kat = (chi2, parameters), asserted by the reference at 1e-12.
 NESTED_SCENARIOS = [
-    dict(name="nested_integral_y1y2x1x2", lines="249-291", active=(1, 1, 1, 1, 1), limit=2,
-         kat=(0.2131810550497416, [15.26735468164642, 1.386383105456653, 0.8486391644471797,
-                                   1.674240469615365, 0.1885677628244937, 1.941800275111635])),
-    dict(name="nested_integral_x1x2", lines="505-547", active=(1, 0, 0, 0, 1), limit=2,
-         kat=(0.0638207048968614, [15.54318299637472, 1.337653916227864, 1.2, 2.0, 0.2,
-                                   2.060422119015556])),
-    dict(name="nested_integral_no_active_bounds", lines="874-917", active=(0, 0, 0, 0, 0), limit=1,
+    dict(name="nested_integral_y1y2x1x2", section="Active bounds: y1 y2 x1 x2", lines="249", active=(1, 1, 1, 1, 1), limit=2,
+         kat=(0.2131810550497416, [15.26735468164642, 1.386383105456653, 0.8486391644471797, 1.674240469615365, 0.1885677628244937, 1.941800275111635])),
+    dict(name="nested_integral_y1y2x1", section="Active bounds: y1 y2 x1", lines="292", active=(1, 1, 1, 1, 0), limit=2,
+         kat=(20529.86214956253, [9.545073737454485, 1.050947728780064, 1.407011447112184, 2.246597745517819, 0.09581638730674913, 2.1])),
+    dict(name="nested_integral_y1y2x2", section="Active bounds: y1 y2 x2", lines="336", active=(1, 1, 1, 1, 1), limit=2,
+         kat=(8.511262427426729, [31.35420758618348, 1.343236097449233, 0.9880791189004298, 1.915159447508319, 0.6301502301640346, 2.041471780774121])),
+    dict(name="nested_integral_y1y2x1x2", section="Active bounds: y1 x1 x2", lines="379", active=(1, 1, 0, 1, 1), limit=2,
+         kat=(0.5452442448229686, [14.51912799259439, 1.401803657027402, 0.7703969798462069, 2.0, 0.2243476865643863, 1.911960222088238])),
+    dict(name="nested_integral_y2x1x2", section="Active bounds: y2 x1 x2", lines="422", active=(1, 1, 0, 1, 1), limit=2,
+         kat=(0.5452442448229419, [14.51912799259429, 1.401803657027403, 0.7703969798462061, 2.0, 0.2243476865643837, 1.911960222088238])),
+    dict(name="nested_integral_y1y2", section="Active bounds: y1 y2", lines="465", active=(1, 1, 1, 1, 0), limit=2,
+         kat=(31829.01194465925, [8.429293418556341, 1.569188491899031, 1.476297876086944, 2.350856627400455, 0.1445015201991888, 2.1])),
+    dict(name="nested_integral_x1x2", section="Active bounds: x1 x2", lines="505", active=(1, 0, 0, 0, 1), limit=2,
+         kat=(0.0638207048968614, [15.54318299637472, 1.337653916227864, 1.2, 2.0, 0.2, 2.060422119015556])),
+    dict(name="nested_integral_y1y2x2", section="Active bounds: y1 x2", lines="548", active=(1, 1, 0, 1, 1), limit=2,
+         kat=(8.310466833011295, [31.05730169163706, 1.337447872754693, 0.9731467848827562, 2.0, 0.6676623753034178, 2.042477682607804])),
+    dict(name="nested_integral_y2x1", section="Active bounds: y2 x1", lines="591", active=(0, 0, 1, 0, 1), limit=2,
+         kat=(20530.20016213086, [72.09812547421947, 1.3, 1.2, 10.90218525163188, 0.2, 15.56263330043302])),
+    dict(name="nested_integral_y1x1", section="Active bounds: y1 x1", lines="628", active=(1, 1, 0, 0, 1), limit=2,
+         kat=(0.3708459104616477, [13.42618730322273, 1.40787919245722, 0.7574214524465727, 2.0, 0.2, 1.896290194086714])),
+    dict(name="nested_integral_y2x1x2", section="Active bounds: y2 x2", lines="671", active=(1, 1, 0, 0, 1), limit=2,
+         kat=(0.3645778424347108, [13.45556877476804, 1.408061308403743, 0.7570256924263207, 2.0, 0.2, 1.895981142726112])),
+    dict(name="nested_integral_y1", section="Active bounds: y1", lines="714", active=(1, 0, 0, 0, 0), limit=2,
+         kat=(33404.97047824427, [18.74611668457635, 3.127350705902004, 1.2, 2.0, 0.2, 2.1])),
+    dict(name="nested_integral_y2", section="Active bounds: y2", lines="754", active=(1, 0, 0, 0, 0), limit=2,
+         kat=(33404.97047824427, [18.74611668457635, 3.127350705902005, 1.2, 2.0, 0.2, 2.1])),
+    dict(name="nested_integral_x1", section="Active bounds: x1", lines="794", active=(0, 0, 0, 0, 1), limit=2,
+         kat=(20529.86874184859, [80.95988477911882, 1.3, 1.2, 2.0, 0.2, 15.63231901313966])),
+    dict(name="nested_integral_y1", section="Active bounds: x2", lines="834", active=(0, 0, 0, 0, 1), limit=2,
+         kat=(20529.86896231501, [80.95988738910319, 1.3, 1.2, 2.0, 0.2, 15.63232441412172])),
+    dict(name="nested_integral_no_active_bounds", section="No active bounds", lines="874", active=(0, 0, 0, 0, 0), limit=1,
          kat=(158.6303014282949, [24.35593003546224, 1.3, 1.2, 2.0, 0.2, 2.1])),
 ]
+for _s in NESTED_SCENARIOS:
+    _s["id"] = "nested:" + _s["section"].replace("Active bounds: ", "").replace(" ", "")
 
 
 def run_nested(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1) -> dict:

@@ -54,26 +54,26 @@ def test_device_adaptive_integration_known_answers(sc, c1):
 
 def _check_nested(rec, sc, rtol):
     chi2, pars = sc["kat"]
-    msg = f"{sc['name']} (numerical_integration.cpp:{sc['lines']})"
+    msg = f"{sc['id']} (numerical_integration.cpp:{sc['lines']})"
     np.testing.assert_allclose(rec["chi2"], chi2, rtol=rtol, err_msg=msg)
     np.testing.assert_allclose(rec["pars"][0], pars, rtol=rtol, err_msg=msg)
     assert rec["iterations"] == sc["limit"]
 
 
-@pytest.mark.parametrize("sc", scenarios.NESTED_SCENARIOS, ids=lambda s: s["name"])
+@pytest.mark.parametrize("sc", scenarios.NESTED_SCENARIOS, ids=lambda s: s["id"])
 def test_oracle_reproduces_nested_integral_known_answers(sc, c1):
     """The reference asserts these at 1e-12."""
     _check_nested(scenarios.run_nested(sc, backends.oracle_solver(1), c1), sc, rtol=1e-12)
 
 
 @pytest.mark.skipif(not backends.has_ref(), reason="oracle/_ref not built (no /root/reference)")
-@pytest.mark.parametrize("sc", scenarios.NESTED_SCENARIOS, ids=lambda s: s["name"])
+@pytest.mark.parametrize("sc", scenarios.NESTED_SCENARIOS, ids=lambda s: s["id"])
 def test_compiled_reference_reproduces_nested_integral_known_answers(sc, c1):
     _check_nested(scenarios.run_nested(sc, backends.ref_solver(), c1), sc, rtol=1e-12)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sc", scenarios.NESTED_SCENARIOS, ids=lambda s: s["name"])
+@pytest.mark.parametrize("sc", scenarios.NESTED_SCENARIOS, ids=lambda s: s["id"])
 def test_device_nested_adaptive_integration_known_answers(sc, c1):
     """An adaptive integral inside the integrand of an adaptive integral, all
     four bounds AD-valued, on the device (per-thread panel stacks)."""
