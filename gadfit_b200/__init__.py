@@ -10,6 +10,6 @@ from .lm_solver import (  # noqa: F401
     InvalidArgument, LateAddDatasetCall, LMsolver, Loss, NcclError,
     NegativeDegreesOfFreedom, NoFittingParameters, NoGlobalParameters,
     NotAvailable, SetParInvalidIndex, SolverSettings, UninitializedParameter,
-    UnknownModel, UnknownOperation, comm_unique_id, io, measure_fp64_peak,
-    models, partition,
+    UnknownModel, UnknownOperation, comm_unique_id, io, load_models,
+    load_test_models, measure_fp64_peak, models, partition,
 )

@@ -76,7 +76,7 @@ CORE_SYMBOLS = [
     "get_trace", "n_iterations", "get_timings", "last_error",
 ]
 PRODUCT_ONLY_SYMBOLS = [
-    "n_models", "model_info", "n_launches", "jacobian_kernel_time",
+    "n_models", "model_info", "load_models", "n_launches", "jacobian_kernel_time",
     "status_name", "set_device", "upload", "comm_unique_id", "set_comm",
     "partition", "measure_fp64_peak", "microbench", "comm_stats",
 ]
@@ -119,6 +119,7 @@ class Api:
             sig.update({
                 "n_models": ([], C.c_int),
                 "model_info": ([C.c_int, C.POINTER(C.c_char_p), c_int_p], C.c_int),
+                "load_models": ([C.c_char_p], C.c_int),
                 "n_launches": ([vp, C.POINTER(C.c_longlong)], C.c_int),
                 "jacobian_kernel_time": ([vp, c_double_p, c_int_p], C.c_int),
                 "status_name": ([C.c_int], C.c_char_p),

@@ -19,7 +19,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libgadfit_b200.so")
-N_MODEL_GROUPS = 30  # models::n_model_groups in include/gadfit_b200/fit_models.h
+N_MODEL_GROUPS = 3  # models::n_model_groups in include/gadfit_b200/fit_models.h
+N_TEST_MODELS = 27  # models::n_test_models in include/gadfit_b200/test_models.h
+TEST_MODELS_OUT = os.path.join(HERE, "libgadfit_b200_testmodels.so")
 
 NVCC_FLAGS = [
     "-std=c++20", "-O3", "-lineinfo",
@@ -73,12 +75,12 @@ def needs_build() -> bool:
     return _stale(OUT, deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
-    if not force and not needs_build():
-        return OUT
+def _compile_and_link(units, out, force, verbose, extra, libs, lineinfo=True):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     common = [*NVCC_FLAGS, *(extra or []), "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if not lineinfo:
+        common.remove("-lineinfo")
     if verbose:
         common.insert(0, "-Xptxas=-v")
     headers = _headers() + [__file__]
@@ -94,15 +96,58 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
         return r.stderr
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-        logs = list(pool.map(compile_unit, _units()))
+        logs = list(pool.map(compile_unit, units))
     if verbose:
         sys.stderr.write("".join(logs))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-            *[u[1] for u in _units()], "-o", OUT, "-ldl"]
+            *[u[1] for u in units], "-o", out, *libs]
     subprocess.run(link, check=True, env=_env())
-    return OUT
+    return out
+
+
+def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
+    """libgadfit_b200.so: solver, kernels of the built-in fitting functions."""
+    if not force and not needs_build():
+        return OUT
+    return _compile_and_link(_units(), OUT, force, verbose, extra, ["-ldl"])
+
+
+def build_plugin(sources: list[str], out: str, force: bool = True, verbose: bool = False,
+                 extra: list[str] | None = None) -> str:
+    """A model plug-in (include/gadfit_b200/model_plugin.h) from user .cu files."""
+    tag = os.path.splitext(os.path.basename(out))[0]
+    units = [(os.path.abspath(src), os.path.join(OBJ, f"{tag}_{i}.o"), [])
+             for i, src in enumerate(sources)]
+    return _compile_and_link(units, os.path.abspath(out), force, verbose, extra, [])
+
+
+def _test_model_units():
+    src = os.path.join(CSRC, "test_models_plugin.cu")
+    return [(src, os.path.join(OBJ, f"test_model_{k}.o"), [f"-DGADFIT_TEST_MODEL={k}"])
+            for k in range(N_TEST_MODELS)]
+
+
+def build_test_models(force: bool = False, verbose: bool = False) -> str:
+    """libgadfit_b200_testmodels.so: the plug-in with the functions of the
+    reference's nested / direct double-integral tests (test_models.h).  Built
+    without -lineinfo: these 27 template-heavy functions are parity fixtures,
+    not profiling targets, and line tables triple the size of the library that
+    every gpurun call has to ship (187 MB -> 60 MB)."""
+    units = _test_model_units()
+    deps = _headers() + [__file__, units[0][0]]
+    if not force and not _stale(TEST_MODELS_OUT, deps):
+        return TEST_MODELS_OUT
+    return _compile_and_link(units, TEST_MODELS_OUT, force, verbose, None, [], lineinfo=False)
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(OUT)
+    if "--plugin" in sys.argv:
+        # python -m gadfit_b200.build --plugin a.cu [b.cu ...] -o libmy_models.so
+        args = sys.argv[sys.argv.index("--plugin") + 1:]
+        out = args[args.index("-o") + 1]
+        srcs = [a for a in args[:args.index("-o")] if a.endswith(".cu")]
+        print(build_plugin(srcs, out, verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+        if "--test-models" in sys.argv:
+            print(build_test_models(force="--force" in sys.argv, verbose="-v" in sys.argv))

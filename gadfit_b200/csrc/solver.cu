@@ -9,11 +9,15 @@
 // per trial step to know which phase to launch next and to keep the trace.
 
 #include "model_ops.cuh"
+#include "plugin_abi.cuh"
 #include "peer_reduce.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string_view>
 #include <numeric>
 
 namespace gadfit_b200 {
@@ -1336,19 +1340,77 @@ auto guarded(gadfit_b200_solver* h, F&& f) -> int
 
 struct ModelInfo
 {
-    const char* name;
+    const char* name; // static storage of the library / the plug-in
     int n_pars;
+    void* (*make_indexed)(int); // plug-in factory; nullptr for built-in functions
+    int plugin_index;
 };
 
-auto model_table() -> const std::vector<ModelInfo>&
+// Built-in functions first, then those of the loaded plug-ins
+// (gadfit_b200_load_models) in loading order
+struct ModelRegistry
 {
-    static const std::vector<ModelInfo> table { [] {
-        std::vector<ModelInfo> t;
-        models::for_each_model(
-          [&]<class Model>() { t.push_back({ Model::name, Model::n_pars }); });
-        return t;
-    }() };
-    return table;
+    std::mutex mutex;
+    std::vector<ModelInfo> table;
+    std::vector<void*> libraries;
+    ModelRegistry()
+    {
+        models::for_each_model([&]<class Model>() {
+            table.push_back({ Model::name, Model::n_pars, nullptr, -1 });
+        });
+    }
+};
+
+auto model_registry() -> ModelRegistry&
+{
+    static ModelRegistry registry;
+    return registry;
+}
+
+// include/gadfit_b200/model_plugin.h
+auto load_models(const char* path) -> int
+{
+    auto& reg { model_registry() };
+    const std::lock_guard lock { reg.mutex };
+    void* lib { dlopen(path, RTLD_NOW | RTLD_LOCAL) };
+    if (lib == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    for (void* known : reg.libraries) {
+        if (known == lib) {
+            dlclose(lib); // already loaded: drop the extra reference
+            return GADFIT_B200_OK;
+        }
+    }
+    const auto abi { reinterpret_cast<long long (*)()>(dlsym(lib, "gadfit_b200_plugin_abi")) };
+    const auto count { reinterpret_cast<int (*)()>(dlsym(lib, "gadfit_b200_plugin_n_models")) };
+    const auto info { reinterpret_cast<int (*)(int, const char**, int*)>(
+      dlsym(lib, "gadfit_b200_plugin_model_info")) };
+    const auto make { reinterpret_cast<void* (*)(int)>(dlsym(lib, "gadfit_b200_plugin_make")) };
+    if (abi == nullptr || count == nullptr || info == nullptr || make == nullptr
+        || abi() != plugin::abi_fingerprint()) {
+        dlclose(lib);
+        return GADFIT_B200_INVALID_ARGUMENT; // not a plug-in, or built against other headers
+    }
+    std::vector<ModelInfo> added;
+    for (int i = 0; i < count(); ++i) {
+        const char* name { nullptr };
+        int n_pars { 0 };
+        if (info(i, &name, &n_pars) != 0 || name == nullptr || n_pars < 1 || n_pars > kMaxShared) {
+            dlclose(lib);
+            return GADFIT_B200_INVALID_ARGUMENT;
+        }
+        for (const auto& m : reg.table) {
+            if (std::string_view { m.name } == name) {
+                dlclose(lib);
+                return GADFIT_B200_INVALID_ARGUMENT; // name already taken
+            }
+        }
+        added.push_back({ name, n_pars, make, i });
+    }
+    reg.table.insert(reg.table.end(), added.begin(), added.end());
+    reg.libraries.push_back(lib);
+    return GADFIT_B200_OK;
 }
 
 } // namespace
@@ -1358,16 +1420,33 @@ extern "C" {
 
 int gadfit_b200_n_models(void)
 {
-    return static_cast<int>(model_table().size());
+    auto& reg { model_registry() };
+    const std::lock_guard lock { reg.mutex };
+    return static_cast<int>(reg.table.size());
+}
+
+int gadfit_b200_load_models(const char* path)
+{
+    if (path == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    try {
+        return load_models(path);
+    } catch (const std::exception&) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
 }
 
 int gadfit_b200_model_info(int i_model, const char** name, int* n_pars)
 {
-    if (i_model < 0 || i_model >= gadfit_b200_n_models()) {
+    auto& reg { model_registry() };
+    const std::lock_guard lock { reg.mutex };
+    if (i_model < 0 || i_model >= static_cast<int>(reg.table.size()) || name == nullptr
+        || n_pars == nullptr) {
         return GADFIT_B200_INVALID_ARGUMENT;
     }
-    *name = model_table()[i_model].name;
-    *n_pars = model_table()[i_model].n_pars;
+    *name = reg.table[i_model].name;
+    *n_pars = reg.table[i_model].n_pars;
     return GADFIT_B200_OK;
 }
 
@@ -1384,6 +1463,16 @@ int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out)
                 ops = make_model_ops_group<G>(model_name);
             }
         });
+        if (!ops) { // a plug-in function?
+            auto& reg { model_registry() };
+            const std::lock_guard lock { reg.mutex };
+            for (const auto& m : reg.table) {
+                if (m.make_indexed != nullptr && std::string_view { m.name } == model_name) {
+                    ops.reset(static_cast<ModelOps*>(m.make_indexed(m.plugin_index)));
+                    break;
+                }
+            }
+        }
         if (!ops) {
             return GADFIT_B200_UNKNOWN_MODEL;
         }

@@ -16,6 +16,7 @@ in the CUDA library; this file only marshals pointers.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -383,6 +384,29 @@ def measure_fp64_peak() -> float:
     if status != _capi.OK:
         raise CudaError(f"status {status}")
     return out.value
+
+
+def load_models(path: str) -> None:
+    """Load a model plug-in (include/gadfit_b200/model_plugin.h): user-defined
+    fitting functions compiled by `python -m gadfit_b200.build --plugin`; they
+    become available to LMsolver(name).  The counterpart of handing the
+    reference an arbitrary lambda (lm_solver.h:146-148)."""
+    status = _capi.product_api().load_models(os.fspath(path).encode())
+    if status != _capi.OK:
+        raise InvalidArgument(
+            f"{path}: cannot be loaded, is not a model plug-in built against these "
+            f"headers, or registers a name that is already taken")
+
+
+def load_test_models() -> None:
+    """The plug-in with the functions of the reference's nested and direct
+    double-integral tests (include/gadfit_b200/test_models.h)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "libgadfit_b200_testmodels.so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    load_models(path)
 
 
 def models() -> dict[str, int]:

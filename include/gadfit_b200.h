@@ -116,14 +116,25 @@ typedef struct gadfit_b200_timings
 
 /* LMsolver::LMsolver(fitSignature), lm_solver.h:148.  The fitting function is
  * selected by name from the functions compiled into the library
- * (include/gadfit_b200/fit_models.h); a std::function cannot run on the
- * device. */
+ * (include/gadfit_b200/fit_models.h) or into a loaded model plug-in; a
+ * std::function cannot run on the device. */
 GADFIT_B200_API int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out);
 GADFIT_B200_API int gadfit_b200_destroy(gadfit_b200_solver* solver);
 
 /* Number of registered fitting functions / name and parameter count of one */
 GADFIT_B200_API int gadfit_b200_n_models(void);
 GADFIT_B200_API int gadfit_b200_model_info(int i_model, const char** name, int* n_pars);
+
+/* User-defined fitting functions -- the counterpart of handing the reference
+ * an arbitrary lambda (lm_solver.h:146-148, c++/tests/example.cpp:11-19).
+ * Loads a model plug-in: a shared library built by nvcc from functors
+ * registered with GADFIT_B200_REGISTER_MODEL
+ * (include/gadfit_b200/model_plugin.h; `python -m gadfit_b200.build --plugin`).
+ * Its functions become available to gadfit_b200_create under their names.
+ * GADFIT_B200_INVALID_ARGUMENT: not loadable, not a plug-in, built against
+ * different headers, or a name is already registered.  Loading the same
+ * library twice is a no-op.  Needs no GPU. */
+GADFIT_B200_API int gadfit_b200_load_models(const char* plugin_path);
 
 /* LMsolver::addDataset(n, x, y, errors = nullptr), lm_solver.h:164-167,
  * lm_solver.cpp:30-56.  Arrays are BORROWED until fit() has uploaded them

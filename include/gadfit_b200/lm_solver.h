@@ -13,9 +13,13 @@
 //
 // changes in exactly one place: the fitting function is named instead of
 // passed as a std::function, because it has to be compiled for the device
-// (see include/gadfit_b200/fit_models.h):
+// (built in: include/gadfit_b200/fit_models.h; the user's own: a model
+// plug-in, include/gadfit_b200/model_plugin.h):
 //
 //     gadfit::LMsolver solver { "exponential" };
+//
+//     gadfit::loadModels("libmy_models.so");        // user-defined functions
+//     gadfit::LMsolver solver2 { "my_function" };
 //
 // Link with -lgadfit_b200.  Nothing here computes: every call forwards.
 #pragma once
@@ -64,6 +68,18 @@ GADFIT_B200_DEFINE_EXCEPTION(DeviceError);
 GADFIT_B200_DEFINE_EXCEPTION(InvalidArgument);
 GADFIT_B200_DEFINE_EXCEPTION(NotAvailable);
 #undef GADFIT_B200_DEFINE_EXCEPTION
+
+// Makes the fitting functions of a model plug-in available by name
+// (gadfit_b200_load_models): the user's functor takes the place of the
+// reference's fitSignature lambda, lm_solver.h:146-148.
+inline auto loadModels(const std::string& plugin_path) -> void
+{
+    if (gadfit_b200_load_models(plugin_path.c_str()) != GADFIT_B200_OK) {
+        throw InvalidArgument { plugin_path
+                                + ": not loadable, not a model plug-in built against these "
+                                  "headers, or a function name is already registered" };
+    }
+}
 
 // ---- IO flags and loss functions (lm_solver.h:60-82) -----------------------
 namespace io {

@@ -24,6 +24,7 @@
 
 #include "gadfit_b200.h"
 #include "gadfit_b200/fit_models.h"
+#include "gadfit_b200/test_models.h"
 #include "oracle_ad.h"
 
 #include <algorithm>
@@ -753,14 +754,16 @@ extern "C" {
 int gadfit_oracle_create(const char* model_name, OracleSolver** out)
 {
     auto solver { std::make_unique<OracleSolver>() };
-    gadfit_b200::models::for_each_model([&]<class Model>() {
+    const auto match { [&]<class Model>() {
         if (std::strcmp(model_name, Model::name) == 0) {
             solver->NP = Model::n_pars;
             solver->body = [](const FVar* p, double x) {
                 return FVar { Model {}(gadfit_oracle::Ctx { p, Model::n_pars }, x) };
             };
         }
-    });
+    } };
+    gadfit_b200::models::for_each_model(match);
+    gadfit_b200::models::for_each_test_model(match);
     if (!solver->body) {
         return GADFIT_B200_UNKNOWN_MODEL;
     }

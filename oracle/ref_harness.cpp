@@ -25,6 +25,7 @@
 
 #include "gadfit_b200.h"
 #include "gadfit_b200/fit_models.h"
+#include "gadfit_b200/test_models.h"
 
 #include <cstring>
 #include <memory>
@@ -186,12 +187,14 @@ int gadfit_ref_create(const char* model_name, RefSolver** out)
         integration_ready = true;
     }
     std::unique_ptr<gadfit::LMsolver> solver;
-    gadfit_b200::models::for_each_model([&]<class Model>() {
+    const auto match { [&]<class Model>() {
         if (std::strcmp(model_name, Model::name) == 0) {
             solver =
               std::make_unique<gadfit::LMsolver>(makeSignature<Model>());
         }
-    });
+    } };
+    gadfit_b200::models::for_each_model(match);
+    gadfit_b200::models::for_each_test_model(match);
     if (!solver) {
         return GADFIT_B200_UNKNOWN_MODEL;
     }

@@ -63,4 +63,8 @@ def ref_solver():
 
 
 def product_solver():
+    """The CUDA library; the functions of the reference's nested / direct
+    double-integral tests come from the test-model plug-in."""
+    import gadfit_b200
+    gadfit_b200.load_test_models()
     return lambda model: LMsolver(model)

@@ -40,6 +40,21 @@ int main(int argc, char** argv)
         ++caught;
     }
     std::printf("caught %d\n", caught);
+    if (argc > 2) { // argv[2]: a model plug-in; its functions become constructible
+        try {
+            gadfit::LMsolver early { "direct_integral_y1" };
+            std::printf("plugin function known before loading\n");
+        } catch (const gadfit::UnknownModel&) {
+            gadfit::loadModels(argv[2]);
+            gadfit::LMsolver late { "direct_integral_y1" };
+            std::printf("plugin loaded\n");
+        }
+        try {
+            gadfit::loadModels("/nonexistent/libmodels.so");
+        } catch (const gadfit::InvalidArgument&) {
+            std::printf("bad plugin rejected\n");
+        }
+    }
     if (argc > 1 && std::strcmp(argv[1], "fit") == 0) {
         solver.settings.iteration_limit = 6;
         solver.settings.acceleration_threshold = 0.9;

@@ -27,9 +27,12 @@ def exe(tmp_path_factory):
 
 
 def test_cpp_wrapper_compiles_and_enforces_call_order(exe):
-    r = subprocess.run([exe, "host"], capture_output=True, text=True)
+    plugin = os.path.join(ROOT, "gadfit_b200", "libgadfit_b200_testmodels.so")
+    r = subprocess.run([exe, "host", plugin], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "caught 3" in r.stdout
+    # gadfit::loadModels: user-defined functions from a model plug-in
+    assert "plugin loaded" in r.stdout and "bad plugin rejected" in r.stdout
 
 
 @pytest.mark.gpu

@@ -1,0 +1,97 @@
+"""User-defined fitting functions through model plug-ins
+(include/gadfit_b200/model_plugin.h, gadfit_b200_load_models): the counterpart
+of handing the reference's LMsolver an arbitrary lambda (lm_solver.h:146-148,
+c++/tests/example.cpp:11-19)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import backends
+import scenarios
+import gadfit_b200 as g
+from gadfit_b200 import build as gbuild
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "user_models_plugin.cu")
+OUT = os.path.join(HERE, "_build", "libuser_models.so")
+
+
+@pytest.fixture(scope="module")
+def user_plugin():
+    """Built with the documented command line; the artefact travels to the GPU
+    box with the snapshot, so it is only rebuilt when stale."""
+    deps = [SRC, os.path.join(gbuild.ROOT, "include", "gadfit_b200", "model_plugin.h"),
+            os.path.join(gbuild.CSRC, "sweep_kernels.cuh"), os.path.join(gbuild.CSRC, "model_ops.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.run([sys.executable, "-m", "gadfit_b200.build", "--plugin", SRC, "-o", OUT],
+                       check=True, cwd=gbuild.ROOT)
+    g.load_models(OUT)
+    return OUT
+
+
+def test_plugin_registers_its_functions_without_a_gpu(user_plugin):
+    registered = g.models()
+    assert registered["user_decay"] == 3
+    assert registered["user_stretched_integral"] == 4
+    g.load_models(user_plugin)  # loading twice is a no-op
+    assert list(g.models()).count("user_decay") == 1
+    s = g.LMsolver("user_decay")  # host-side bookkeeping works without a device
+    s.addDataset(np.arange(4.0), np.arange(4.0))
+    s.setPar(0, 1.0, True)
+    with pytest.raises(g.UnknownModel):
+        g.LMsolver("user_decay_typo")
+
+
+def test_loading_something_that_is_not_a_plugin_fails_cleanly(tmp_path):
+    with pytest.raises(g.InvalidArgument):
+        g.load_models(str(tmp_path / "does_not_exist.so"))
+    oracle_lib = backends.oracle_api().path  # a shared library, but no plug-in
+    with pytest.raises(g.InvalidArgument):
+        g.load_models(oracle_lib)
+
+
+def test_test_model_plugin_provides_the_integration_test_functions():
+    g.load_test_models()
+    registered = g.models()
+    assert sum(k.startswith("nested_integral_") for k in registered) == 12
+    assert sum(k.startswith("direct_integral_") for k in registered) == 15
+    assert registered["direct_integral_y1y2x1x2"] == 7 and registered["nested_integral_x1x2"] == 6
+
+
+@pytest.mark.gpu
+def test_user_function_reproduces_the_builtin_known_answers(user_plugin, c1):
+    """The same functor body, compiled in a plug-in under a user's name, gives
+    bit-identical results to the built-in one and hence the reference's known
+    answers (c++/tests/lm_solver.cpp:21-47)."""
+    sc = scenarios.C1_SCENARIOS[0]
+    builtin, _ = scenarios.run(sc, lambda _m: g.LMsolver("exponential"), c1)
+    user, _ = scenarios.run(sc, lambda _m: g.LMsolver("user_decay"), c1)
+    assert builtin["chi2"] == user["chi2"] and builtin["pars"] == user["pars"]
+    assert [t["new_chi2"] for t in builtin["trace"]] == [t["new_chi2"] for t in user["trace"]]
+    np.testing.assert_allclose(user["chi2"], sc["kat"][0], rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_user_function_with_adaptive_integral_recovers_its_parameters(user_plugin):
+    """A function the library has never seen (adaptive integral with the data
+    point as upper bound, pow/exp inside): fit noise-free synthetic data."""
+    from scipy.integrate import quad
+    truth = (2.0, 1.5, 0.8, 0.3)
+    x = np.linspace(0.2, 6.0, 120)
+    y = np.array([truth[0] * quad(lambda t: np.exp(-(t / truth[1]) ** truth[2]), 0.0, xi,
+                                  epsabs=1e-13, epsrel=1e-13)[0] + truth[3] for xi in x])
+    s = g.LMsolver("user_stretched_integral")
+    s.addDataset(x, y)
+    for k, v in enumerate((1.5, 1.2, 1.0, 0.1)):
+        s.setPar(k, v, True)
+    s.settings.iteration_limit = 50
+    s.fit(1.0)
+    got = [s.getParValue(k) for k in range(4)]
+    np.testing.assert_allclose(got, truth, rtol=1e-6)
+    assert s.chi2() < 1e-14
+    np.testing.assert_allclose(s.getValue(3.0), truth[0] * quad(
+        lambda t: np.exp(-(t / truth[1]) ** truth[2]), 0.0, 3.0)[0] + truth[3], rtol=1e-7)
