@@ -6,7 +6,7 @@ Host side only: ``LMsolver`` mirrors ``gadfit::LMsolver``; all arithmetic is in
 ``__graft_entry__.build()``).  There is no CPU fallback.
 """
 from .lm_solver import (  # noqa: F401
-    CudaError, GADfitException, InsufficientIntegrationWorkspace,
+    CudaError, GADfitException, GadfOptions, InsufficientIntegrationWorkspace,
     InvalidArgument, LateAddDatasetCall, LMsolver, Loss, NcclError,
     NegativeDegreesOfFreedom, NoFittingParameters, NoGlobalParameters,
     NotAvailable, SetParInvalidIndex, SolverSettings, UninitializedParameter,

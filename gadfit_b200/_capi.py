@@ -46,6 +46,22 @@ class Trial(C.Structure):
     ]
 
 
+class GadfOptions(C.Structure):
+    """gadfit_b200_gadf_options: the Fortran-only arguments of gadf_fit"""
+    _fields_ = [
+        ("enabled", C.c_int),
+        ("uphill", C.c_int),
+        ("nielsen", C.c_int),
+        ("umnigh", C.c_int),
+        ("chi2_abs", C.c_double),
+        ("chi2_rel", C.c_double),
+        ("grad_chi2", C.c_double),
+        ("cos_phi", C.c_double),
+        ("rel_error", C.c_double),
+        ("rel_error_global", C.c_double),
+    ]
+
+
 class Timings(C.Structure):
     _fields_ = [("seconds", C.c_double * 5), ("calls", C.c_int * 5)]
 
@@ -76,6 +92,7 @@ CORE_SYMBOLS = [
     "get_trace", "n_iterations", "get_timings", "last_error",
 ]
 PRODUCT_ONLY_SYMBOLS = [
+    "default_gadf_options", "set_gadf_options", "get_stop_reason",
     "n_models", "model_info", "load_models", "n_launches", "jacobian_kernel_time",
     "status_name", "set_device", "upload", "comm_unique_id", "set_comm",
     "partition", "measure_fp64_peak", "microbench", "comm_stats",
@@ -115,6 +132,13 @@ class Api:
             "get_timings": ([vp, C.POINTER(Timings)], C.c_int),
             "last_error": ([vp], C.c_char_p),
         }
+        self.has_gadf = product or prefix == "gadfit_oracle_"
+        if self.has_gadf:
+            sig.update({
+                "default_gadf_options": ([C.POINTER(GadfOptions)], C.c_int),
+                "set_gadf_options": ([vp, C.POINTER(GadfOptions)], C.c_int),
+                "get_stop_reason": ([vp, c_int_p], C.c_int),
+            })
         if product:
             sig.update({
                 "n_models": ([], C.c_int),

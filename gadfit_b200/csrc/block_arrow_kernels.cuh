@@ -604,4 +604,102 @@ static __global__ void k_revert_if_rejected(const long long n,
     }
 }
 
+// ---- the Fortran driver gadf_fit (fortran/gadfit/gadfit.F90:751-909) --------
+//
+// Scalars its accept test, lambda updates and convergence tests need, as sums
+// over the active parameters (every global parameter counted once):
+//   [0] delta1' D delta1       [1] delta1' D old_delta1   [2] old_delta1' D old_delta1
+//   [3] delta1' J^T r          [4] |J^T r|^2
+//   [5] #{ |delta1 / parameter| > rel_error }             (:882-894)
+//   [6] #{ the same over global parameters, rel_error_global }  (:895-903)
+//   [7] |r|^2 at the Jacobian point
+constexpr int kGadfSums { 8 };
+
+// One thread per data set: the local parameters' share
+static __global__ void k_gadf_local(const int NP,
+                                    const double* __restrict__ M,
+                                    const unsigned* __restrict__ active,
+                                    const unsigned global_mask,
+                                    const int n_sets,
+                                    const double* __restrict__ dtd_local,
+                                    const double* __restrict__ delta1_par,
+                                    const double* __restrict__ old_delta1_par,
+                                    const double* __restrict__ par,
+                                    const double rel_error,
+                                    double* __restrict__ contrib)
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    const int NA { NP + 1 };
+    const int NT { NA * (NA + 1) / 2 };
+    const double* Ms { M + static_cast<long long>(s) * NT };
+    const unsigned local { active[s] & ~global_mask };
+    double sums[kGadfSums] {};
+    for (int k = 0; k < NP; ++k) {
+        if (((local >> k) & 1U) != 0U) {
+            const long long o { static_cast<long long>(s) * NP + k };
+            const double D { dtd_local[o] };
+            const double d1 { delta1_par[o] };
+            const double d0 { old_delta1_par[o] };
+            const double rhs { Ms[tri_index(NA, k, NP)] };
+            sums[0] += d1 * (D * d1);
+            sums[1] += d1 * (D * d0);
+            sums[2] += d0 * (D * d0);
+            sums[3] += d1 * rhs;
+            sums[4] += rhs * rhs;
+            if (rel_error >= 0.0 && fabs(d1 / par[o]) > rel_error) {
+                sums[5] += 1.0;
+            }
+        }
+    }
+    sums[7] = Ms[tri_index(NA, NP, NP)];
+    for (int j = 0; j < kGadfSums; ++j) {
+        contrib[static_cast<long long>(s) * kGadfSums + j] = sums[j];
+    }
+}
+
+// The global parameters' share, added by one thread on the rank that owns
+// data set 0 (par_set0 = its parameter vector)
+static __global__ void k_gadf_global(const int NP,
+                                     const int pg,
+                                     const unsigned global_mask,
+                                     const double* __restrict__ shared_sums,
+                                     const double* __restrict__ dtd_global,
+                                     const double* __restrict__ delta1_g,
+                                     const double* __restrict__ old_delta1_g,
+                                     const double* __restrict__ par_set0,
+                                     const double rel_error,
+                                     const double rel_error_global,
+                                     double* __restrict__ sums)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    int a { 0 };
+    for (int k = 0; k < NP; ++k) {
+        if (((global_mask >> k) & 1U) == 0U) {
+            continue;
+        }
+        const double D { dtd_global[a] };
+        const double d1 { delta1_g[a] };
+        const double d0 { old_delta1_g[a] };
+        const double rhs { shared_sums[pg * (pg + 1) / 2 + a] };
+        sums[0] += d1 * (D * d1);
+        sums[1] += d1 * (D * d0);
+        sums[2] += d0 * (D * d0);
+        sums[3] += d1 * rhs;
+        sums[4] += rhs * rhs;
+        const double rel { fabs(d1 / par_set0[k]) };
+        if (rel_error >= 0.0 && rel > rel_error) {
+            sums[5] += 1.0;
+        }
+        if (rel_error_global >= 0.0 && rel > rel_error_global) {
+            sums[6] += 1.0;
+        }
+        ++a;
+    }
+}
+
 } // namespace gadfit_b200

@@ -227,6 +227,13 @@ struct SolverImpl
     bool fitted { false };
     double lambda_lhs { 0.0 };      // lambda of the last left-hand side
     bool have_delta2 { false };
+    // the Fortran driver (gadfit_b200_gadf_options)
+    gadfit_b200_gadf_options gadf { 0, 0, 0, 0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0 };
+    double umnigh_a { 0.5 }; // gadfit.F90:515, a saved variable: persists across fits
+    int stop_reason { GADFIT_B200_STOP_ITERATION_LIMIT };
+    DeviceBuffer<double> d_old_delta1_par;
+    DeviceBuffer<double> d_old_delta1_g;
+    DeviceBuffer<double> d_gadf_sums;
     PhaseTimer t_jacobian, t_chi2, t_linalg, t_omega, t_main, t_jac_kernel;
 
     ~SolverImpl()
@@ -391,7 +398,7 @@ struct SolverImpl
         }
         GADFIT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         GADFIT_CUDA_TRY(cudaMallocHost(&h_mirror, 2 * sizeof(LmState)));
-        GADFIT_CUDA_TRY(cudaMallocHost(&h_scalar, 8 * sizeof(double)));
+        GADFIT_CUDA_TRY(cudaMallocHost(&h_scalar, 24 * sizeof(double)));
         ops->init_device();
         d_state.ensure(3);
         d_scratch.ensure(8);
@@ -736,10 +743,12 @@ struct SolverImpl
     }
 
     // computeDeltas (lm_solver.cpp:348-399) followed by updateParameters
-    auto solve_phase(const bool first_trial) -> void
+    // delta1_only: the Fortran driver's re-solve after a rejected step
+    // (gadfit.F90:801-808): no omega sweep, no delta2, update with delta1 alone
+    auto solve_phase(const bool first_trial, const bool delta1_only = false) -> void
     {
         const int VG { shared_len() };
-        const bool accelerate { settings.acceleration_threshold > 0.0 };
+        const bool accelerate { !delta1_only && settings.acceleration_threshold > 0.0 };
         t_linalg.start(stream);
         // No data set has a local parameter (n = p_g, e.g. BASELINE config 2):
         // the Schur complement is empty on every rank, so its kernels and its
@@ -949,6 +958,11 @@ struct SolverImpl
     // LMsolver::fit, lm_solver.cpp:401-511
     auto fit(const double lambda0) -> void
     {
+        if (gadf.enabled != 0) {
+            fit_gadf(lambda0);
+            return;
+        }
+        stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
         prepare_indexing();
         ensure_device();
         upload_parameters();
@@ -1022,6 +1036,7 @@ struct SolverImpl
                 } else {
                     --i_iteration;
                     finished = true;
+                    stop_reason = GADFIT_B200_STOP_LAMBDA_INCS;
                 }
             }
             if (i_iteration == settings.iteration_limit) {
@@ -1030,6 +1045,250 @@ struct SolverImpl
         }
         t_main.stop(stream);
         n_iterations = i_iteration;
+        download_parameters();
+        for (PhaseTimer* t :
+             { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
+            t->collect();
+        }
+        fitted = true;
+    }
+
+    // gadf_fit, fortran/gadfit/gadfit.F90:678-915: the same sweeps and solves,
+    // driven by the Fortran version's accept test, lambda updates, re-solve
+    // rule and convergence tests.  The scalars they need are reduced on the
+    // device (k_gadf_local / k_gadf_global); the decisions are taken on the
+    // host, which reads one small record per trial step anyway.
+    auto fit_gadf(const double lambda0) -> void
+    {
+        if (settings.loss != GADFIT_B200_LOSS_LINEAR) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "gadf_fit has no loss functions" };
+        }
+        prepare_indexing();
+        ensure_device();
+        upload_parameters();
+        reset_timers();
+        init_damping();
+        const size_t n_par { static_cast<size_t>(std::max(n_local_sets, 1)) * NP };
+        d_delta1_par.zero(n_par, stream);
+        d_delta2_par.zero(n_par, stream);
+        d_old_delta1_par.zero(n_par, stream);
+        d_delta1_g.zero(kMaxShared, stream);
+        d_delta2_g.zero(kMaxShared, stream);
+        d_old_delta1_g.zero(kMaxShared, stream);
+        d_gadf_sums.zero(kGadfSums + 1, stream);
+        d_chol.ensure(kMaxShared * kMaxShared);
+        d_factors.ensure(static_cast<size_t>(std::max(n_local_sets, 1)) * ops->factor_bytes());
+        const bool accelerate { settings.acceleration_threshold > 0.0 };
+        have_delta2 = false;
+        trace.clear();
+        n_iterations = 0;
+        stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
+
+        LmState init {};
+        init.lambda = lambda0;
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(
+          d_state.ptr, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
+        double lambda { lambda0 };
+        const auto set_lambda { [&](const double value) {
+            lambda = value;
+            h_scalar[0] = value;
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(&d_state.ptr->lambda,
+                                            h_scalar,
+                                            sizeof(double),
+                                            cudaMemcpyHostToDevice,
+                                            stream));
+            GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        } };
+        const auto revert { [&] {
+            if (n_local_sets > 0) {
+                GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr,
+                                                d_par_old.ptr,
+                                                static_cast<size_t>(n_local_sets) * NP
+                                                  * sizeof(double),
+                                                cudaMemcpyDeviceToDevice,
+                                                stream));
+            }
+        } };
+        // chi2 of the trial parameters + the reduced scalars -> host
+        double* const h_gadf { h_scalar + 8 }; // pinned
+        double sums[kGadfSums + 1] {};
+        const auto measure { [&] {
+            chi2_phase(d_gadf_sums.ptr + kGadfSums);
+            t_linalg.start(stream);
+            d_contrib.ensure(static_cast<size_t>(std::max(n_local_sets, 1))
+                             * std::max(shared_len(), kGadfSums));
+            if (n_local_sets > 0) {
+                k_gadf_local<<<blocks_for(n_local_sets, 128), 128, 0, stream>>>(
+                  NP,
+                  d_M.ptr,
+                  d_active.ptr,
+                  global_mask,
+                  n_local_sets,
+                  d_dtd_local.ptr,
+                  d_delta1_par.ptr,
+                  d_old_delta1_par.ptr,
+                  d_par.ptr,
+                  gadf.rel_error,
+                  d_contrib.ptr);
+                launched();
+            }
+            column_sums(d_contrib.ptr, kGadfSums, d_gadf_sums.ptr);
+            const bool owns_set0 { n_local_sets > 0 && part.first == 0 };
+            if (pg > 0 && owns_set0) {
+                k_gadf_global<<<1, 1, 0, stream>>>(NP,
+                                                   pg,
+                                                   global_mask,
+                                                   d_shared_sums.ptr,
+                                                   d_dtd_global.ptr,
+                                                   d_delta1_g.ptr,
+                                                   d_old_delta1_g.ptr,
+                                                   d_par.ptr,
+                                                   gadf.rel_error,
+                                                   gadf.rel_error_global,
+                                                   d_gadf_sums.ptr);
+                launched();
+            }
+            if (!part.split) {
+                all_reduce(d_gadf_sums.ptr, kGadfSums);
+            }
+            t_linalg.stop(stream);
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(h_gadf,
+                                            d_gadf_sums.ptr,
+                                            (kGadfSums + 1) * sizeof(double),
+                                            cudaMemcpyDeviceToHost,
+                                            stream));
+            GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+            std::copy(h_gadf, h_gadf + kGadfSums + 1, sums);
+        } };
+
+        const double umnigh_m { std::exp(-0.2) }; // :516
+        t_main.start(stream);
+        chi2_phase(d_gadf_sums.ptr + kGadfSums);
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(h_gadf,
+                                        d_gadf_sums.ptr + kGadfSums,
+                                        sizeof(double),
+                                        cudaMemcpyDeviceToHost,
+                                        stream));
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        double old_chi2 { h_gadf[0] };
+        double old_old_chi2 { old_chi2 };
+        int iterations { 0 };
+        bool done { false };
+        while (!done) {
+            // STEP 1-3 (:680-750)
+            jacobian_phase(accelerate, false);
+            lambda_lhs = lambda;
+            double lambda_solved { lambda };
+            solve_phase(true);
+            // STEP 4 (:751-818)
+            double new_chi2 { 0.0 };
+            for (int i = 1; i <= settings.lambda_incs + 1; ++i) {
+                measure();
+                new_chi2 = sums[kGadfSums];
+                trace.push_back({ lambda, new_chi2, old_chi2, iterations + 1, 0 });
+                const double beta { iterations == 0 ? 0.0
+                                                    : sums[1] / std::sqrt(sums[0])
+                                                        / std::sqrt(sums[2]) };
+                double factor { 1.0 };
+                for (int k = 0; k < gadf.uphill; ++k) {
+                    factor *= 1.0 - beta;
+                }
+                if (factor * new_chi2 < old_chi2) {
+                    if (gadf.nielsen != 0) {
+                        // delta1'(JTJ + lambda D) delta1 = delta1' J^T r, :766-769
+                        const double rho { (old_chi2 - new_chi2) / 2 / sums[3] };
+                        const double t { 2 * rho - 1 };
+                        set_lambda(lambda * std::max(1 / settings.lambda_down, 1 - t * t * t));
+                    }
+                    if (gadf.umnigh != 0) { // :771-783
+                        if (new_chi2 < old_chi2 && beta >= 0.0) {
+                            umnigh_a = umnigh_a * umnigh_m + 1.0 - umnigh_m;
+                            const double t { 1.0 - std::abs(2.0 * umnigh_a - 1.0) };
+                            set_lambda(lambda * std::min(1.0, std::max(1e-2, t * t)));
+                        } else {
+                            umnigh_a = umnigh_a * umnigh_m + (1.0 - umnigh_m) / 2.0;
+                            if (new_chi2 >= old_chi2) {
+                                set_lambda(lambda
+                                           / std::min(10.0,
+                                                      std::max(1.0,
+                                                               1.0
+                                                                 - std::abs(2.0 * umnigh_a
+                                                                            - 1.0))));
+                            }
+                        }
+                    }
+                    if (gadf.nielsen == 0 && gadf.umnigh == 0) {
+                        set_lambda(lambda / settings.lambda_down);
+                    }
+                    break;
+                }
+                if (i <= settings.lambda_incs) { // :790-808
+                    trace.back().decision = 1;
+                    if (gadf.umnigh != 0) {
+                        umnigh_a *= umnigh_m;
+                        const double t { 1.0 - std::abs(2.0 * umnigh_a - 1.0) };
+                        set_lambda(lambda
+                                   * (beta < 0.0 ? std::min(1.0, std::max(1e-2, t * t))
+                                                 : std::min(1.0, std::max(0.1, t))));
+                    } else {
+                        set_lambda(settings.lambda_up * lambda);
+                    }
+                    revert();
+                    lambda_lhs = lambda;
+                    lambda_solved = lambda;
+                    solve_phase(false, true);
+                } else { // :809-816
+                    trace.back().decision = 2;
+                    revert();
+                    stop_reason = GADFIT_B200_STOP_LAMBDA_INCS;
+                    done = true;
+                }
+            }
+            if (done) {
+                break;
+            }
+            // :819-824
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_old_delta1_par.ptr,
+                                            d_delta1_par.ptr,
+                                            n_par * sizeof(double),
+                                            cudaMemcpyDeviceToDevice,
+                                            stream));
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_old_delta1_g.ptr,
+                                            d_delta1_g.ptr,
+                                            kMaxShared * sizeof(double),
+                                            cudaMemcpyDeviceToDevice,
+                                            stream));
+            old_old_chi2 = old_chi2;
+            old_chi2 = std::min(old_chi2, new_chi2);
+            ++iterations;
+            // STEP 5 (:832-909), in the Fortran version's order
+            if (gadf.chi2_abs >= 0.0 && old_chi2 / dof < gadf.chi2_abs) {
+                stop_reason = GADFIT_B200_STOP_CHI2_ABS;
+            } else if (gadf.chi2_rel >= 0.0
+                       && (old_old_chi2 - old_chi2) / old_chi2 < gadf.chi2_rel) {
+                stop_reason = GADFIT_B200_STOP_CHI2_REL;
+            } else if (gadf.grad_chi2 >= 0.0 && 2 * std::sqrt(sums[4]) < gadf.grad_chi2) {
+                stop_reason = GADFIT_B200_STOP_GRAD_CHI2;
+            } else if (gadf.cos_phi >= 0.0
+                       // |r'J delta1| / |r| / |J delta1|,  |J delta1|^2 =
+                       // delta1'J^T r - lambda delta1'D delta1
+                       && std::abs(sums[3]) / std::sqrt(sums[7])
+                              / std::sqrt(sums[3] - lambda_solved * sums[0])
+                            < gadf.cos_phi) {
+                stop_reason = GADFIT_B200_STOP_COS_PHI;
+            } else if (gadf.rel_error >= 0.0 && sums[5] == 0.0) {
+                stop_reason = GADFIT_B200_STOP_REL_ERROR;
+            } else if (gadf.rel_error_global >= 0.0 && sums[6] == 0.0) {
+                stop_reason = GADFIT_B200_STOP_REL_ERROR_GLOBAL;
+            } else if (iterations >= settings.iteration_limit) {
+                stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
+            } else {
+                continue;
+            }
+            break;
+        }
+        t_main.stop(stream);
+        n_iterations = iterations;
         download_parameters();
         for (PhaseTimer* t :
              { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
@@ -1555,9 +1814,38 @@ int gadfit_b200_set_settings(gadfit_b200_solver* solver, const gadfit_b200_setti
     });
 }
 
+int gadfit_b200_default_gadf_options(gadfit_b200_gadf_options* out)
+{
+    if (out == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
+    *out = { 0, 0, 0, 0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0 };
+    return GADFIT_B200_OK;
+}
+
+int gadfit_b200_set_gadf_options(gadfit_b200_solver* solver, const gadfit_b200_gadf_options* o)
+{
+    return guarded(solver, [&] {
+        if (o == nullptr || o->uphill < 0) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "invalid gadf options" };
+        }
+        solver->gadf = *o;
+    });
+}
+
 int gadfit_b200_fit(gadfit_b200_solver* solver, double lambda)
 {
     return guarded(solver, [&] { solver->fit(lambda); });
+}
+
+int gadfit_b200_get_stop_reason(gadfit_b200_solver* solver, int* out)
+{
+    return guarded(solver, [&] {
+        if (out == nullptr) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "null output" };
+        }
+        *out = solver->stop_reason;
+    });
 }
 
 int gadfit_b200_get_par(gadfit_b200_solver* solver, int i_par, int i_dataset, double* out)

@@ -23,10 +23,14 @@
 !    converted to the errors the C-ABI expects.
 !  * Defaults are those of the FORTRAN reference, not of the C++ one:
 !    lambda = 1, lam_incs = 2 (gadfit.F90:568-580).
-!  * The Fortran-only options uphill, nielsen, umnigh, the convergence tests
-!    (grad_chi2, cos_phi, rel_error, rel_error_global, chi2_rel, chi2_abs),
-!    load_balancing and use_ad are accepted for source compatibility and
-!    ignored with a warning; file input and gadf_print are not provided.
+!  * fit() runs the FORTRAN driver (gadfit_b200_gadf_options, enabled = 1):
+!    uphill, nielsen, umnigh and the convergence tests (grad_chi2, cos_phi,
+!    rel_error, rel_error_global, chi2_rel, chi2_abs) have the reference's
+!    meaning (gadfit.F90:751-909); gadf_set_errors(NONE / SQRT_Y / PROPTO_Y /
+!    INVERSE_Y / USER) as in gadfit.F90:445-470.
+!  * load_balancing and use_ad are accepted for source compatibility and
+!    ignored (the device always differentiates automatically; work is split
+!    statically); file input and gadf_print are not provided.
 !
 ! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no gfortran.
 ! Build where one exists:  gfortran -c gadfit.F90 && gfortran prog.F90 gadfit.o
@@ -39,8 +43,14 @@ module gadfit
   implicit none
 
   private
-  public :: gadf_init, gadf_add_dataset, gadf_set, gadf_fit, gadf_get, &
-       & gadf_chi2, gadf_iterations, gadf_close, kp
+  public :: gadf_init, gadf_add_dataset, gadf_set, gadf_set_errors, gadf_fit, &
+       & gadf_get, gadf_chi2, gadf_iterations, gadf_stop_reason, gadf_close, kp
+  public :: NONE, SQRT_Y, PROPTO_Y, INVERSE_Y, USER
+
+  ! gadf_constants.F90: data error types
+  enum, bind(c)
+     enumerator :: NONE, SQRT_Y, PROPTO_Y, INVERSE_Y, USER
+  end enum
 
   integer, parameter :: kp = real64
 
@@ -59,7 +69,33 @@ module gadfit
      integer(c_int) :: n_threads
   end type settings_t
 
+  ! POD mirror of gadfit_b200_gadf_options
+  type, bind(c) :: gadf_options_t
+     integer(c_int) :: enabled
+     integer(c_int) :: uphill
+     integer(c_int) :: nielsen
+     integer(c_int) :: umnigh
+     real(c_double) :: chi2_abs
+     real(c_double) :: chi2_rel
+     real(c_double) :: grad_chi2
+     real(c_double) :: cos_phi
+     real(c_double) :: rel_error
+     real(c_double) :: rel_error_global
+  end type gadf_options_t
+
   interface
+     integer(c_int) function c_set_gadf_options(handle, o) &
+          & bind(c, name='gadfit_b200_set_gadf_options')
+       import :: c_int, c_ptr, gadf_options_t
+       type(c_ptr), value :: handle
+       type(gadf_options_t), intent(in) :: o
+     end function c_set_gadf_options
+     integer(c_int) function c_get_stop_reason(handle, reason) &
+          & bind(c, name='gadfit_b200_get_stop_reason')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: handle
+       integer(c_int), intent(out) :: reason
+     end function c_get_stop_reason
      integer(c_int) function c_create(model_name, handle) &
           & bind(c, name='gadfit_b200_create')
        import :: c_int, c_char, c_ptr
@@ -133,9 +169,14 @@ module gadfit
 
   type(c_ptr) :: handle = c_null_ptr
   integer :: num_datasets_expected = 1, num_datasets_added = 0
-  ! Errors handed to the library must outlive gadf_fit: one array per dataset
+  integer :: data_error_type = NONE
+  ! Errors handed to the library must outlive gadf_fit: one array per dataset.
+  ! They are BORROWED by the library until the first fit uploads them, so
+  ! gadf_fit can still fill them according to gadf_set_errors.
   type :: errors_t
      real(kp), allocatable :: sigma(:)
+     real(kp), pointer :: y(:) => null()
+     logical :: user_weights = .false.
   end type errors_t
   type(errors_t), allocatable, target :: errors(:)
 
@@ -187,13 +228,16 @@ contains
        error stop
     end if
     num_datasets_added = num_datasets_added + 1
-    e = c_null_ptr
+    ! sigma is filled in gadf_fit (init_weights, gadfit.F90:445-470); with
+    ! USER errors the third column holds the uncertainties themselves
+    allocate(errors(num_datasets_added)%sigma(size(y_data)))
+    errors(num_datasets_added)%sigma = 1.0_kp
+    errors(num_datasets_added)%y => y_data
     if (present(weights)) then
-       ! the reference multiplies by the weight (gadfit.F90:683,690)
-       allocate(errors(num_datasets_added)%sigma(size(weights)))
-       errors(num_datasets_added)%sigma = 1.0_kp/weights
-       e = c_loc(errors(num_datasets_added)%sigma)
+       errors(num_datasets_added)%sigma = weights
+       errors(num_datasets_added)%user_weights = .true.
     end if
+    e = c_loc(errors(num_datasets_added)%sigma)
     call check(c_add_dataset(handle, int(size(x_data), c_int), c_loc(x_data), &
          & c_loc(y_data), e), 'gadf_add_dataset')
   end subroutine gadf_add_dataset
@@ -235,6 +279,45 @@ contains
     call set_int_global_real(par, real(val, kp), active)
   end subroutine set_int_global_real32
 
+  ! gadfit.F90:391-394
+  subroutine gadf_set_errors(e)
+    integer, intent(in) :: e
+    data_error_type = e
+  end subroutine gadf_set_errors
+
+  ! init_weights, gadfit.F90:445-470, expressed as sigma = 1/weight
+  subroutine init_sigma()
+    integer :: i
+    do i = 1, num_datasets_added
+       associate(sigma => errors(i)%sigma, y => errors(i)%y)
+         select case(data_error_type)
+         case(NONE)
+            sigma = 1.0_kp
+         case(SQRT_Y)
+            where(abs(y) < 1d2*tiny(1.0_kp))
+               sigma = huge(1.0_kp) ! weight 0
+            elsewhere
+               sigma = sqrt(y)
+            end where
+         case(PROPTO_Y)
+            where(abs(y) < 1d2*tiny(1.0_kp))
+               sigma = huge(1.0_kp)
+            elsewhere
+               sigma = y
+            end where
+         case(INVERSE_Y)
+            sigma = 1.0_kp/y
+         case(USER)
+            if (.not. errors(i)%user_weights) then
+               write(error_unit, '(a)') 'gadfit (B200): USER errors need the &
+                    &third argument of gadf_add_dataset'
+               error stop
+            end if
+         end select
+       end associate
+    end do
+  end subroutine init_sigma
+
   ! gadfit.F90:502-511, defaults :568-580
   subroutine gadf_fit(lambda, lam_up, lam_down, accth, grad_chi2, cos_phi, &
        & rel_error, rel_error_global, chi2_rel, chi2_abs, DTD_min, lam_incs, &
@@ -246,8 +329,15 @@ contains
     logical, intent(in), optional :: damp_max, nielsen, umnigh, use_ad
     logical, value, optional :: load_balancing
     type(settings_t) :: s
+    type(gadf_options_t) :: o
     real(kp) :: lambda_loc
+    logical, save :: sigma_ready = .false.
+    if (.not. sigma_ready) then
+       call init_sigma() ! once, like init_weights (gadfit.F90:565-568)
+       sigma_ready = .true.
+    end if
     call check(c_default_settings(s), 'gadf_fit')
+    s%iteration_limit = huge(1_c_int) ! no max_iter: run until a test stops it
     lambda_loc = 1.0_kp
     s%lambda_incs = 2
     if (present(lambda)) lambda_loc = real(lambda, kp)
@@ -261,14 +351,19 @@ contains
        s%DTD_min = c_loc(DTD_min)
        s%n_DTD_min = size(DTD_min)
     end if
-    if (present(grad_chi2) .or. present(cos_phi) .or. present(rel_error) .or. &
-         & present(rel_error_global) .or. present(chi2_rel) .or. &
-         & present(chi2_abs) .or. present(uphill) .or. present(nielsen) .or. &
-         & present(umnigh) .or. present(load_balancing) .or. present(use_ad)) then
-       write(error_unit, '(a)') 'gadfit (B200): warning: Fortran-only LM options &
-            &(uphill, nielsen, umnigh, convergence tests, load_balancing, use_ad) &
-            &are ignored'
-    end if
+    ! the Fortran driver and its own options (gadfit_b200_gadf_options);
+    ! a negative tolerance means "argument absent"
+    o = gadf_options_t(1, 0, 0, 0, -1.0_kp, -1.0_kp, -1.0_kp, -1.0_kp, -1.0_kp, -1.0_kp)
+    if (present(uphill)) o%uphill = uphill
+    if (present(nielsen)) o%nielsen = merge(1, 0, nielsen)
+    if (present(umnigh)) o%umnigh = merge(1, 0, umnigh)
+    if (present(chi2_abs)) o%chi2_abs = real(chi2_abs, kp)
+    if (present(chi2_rel)) o%chi2_rel = real(chi2_rel, kp)
+    if (present(grad_chi2)) o%grad_chi2 = real(grad_chi2, kp)
+    if (present(cos_phi)) o%cos_phi = real(cos_phi, kp)
+    if (present(rel_error)) o%rel_error = real(rel_error, kp)
+    if (present(rel_error_global)) o%rel_error_global = real(rel_error_global, kp)
+    call check(c_set_gadf_options(handle, o), 'gadf_fit')
     call check(c_set_settings(handle, s), 'gadf_fit')
     call check(c_fit(handle, lambda_loc), 'gadf_fit')
   end subroutine gadf_fit
@@ -289,6 +384,14 @@ contains
     call check(c_n_iterations(handle, m), 'gadf_iterations')
     n = m
   end function gadf_iterations
+
+  ! 0 max_iter, 1 lam_incs, 2 chi2_abs, 3 chi2_rel, 4 grad_chi2, 5 cos_phi,
+  ! 6 rel_error, 7 rel_error_global (the messages of gadfit.F90:812-908)
+  integer function gadf_stop_reason() result(reason)
+    integer(c_int) :: r
+    call check(c_get_stop_reason(handle, r), 'gadf_stop_reason')
+    reason = r
+  end function gadf_stop_reason
 
   ! gadfit.F90:1397-1414
   subroutine gadf_close()

@@ -137,6 +137,28 @@ class SolverSettings:
     n_threads: int = 1
 
 
+@dataclass
+class GadfOptions:
+    """The arguments that exist only in the Fortran driver gadf_fit
+    (fortran/gadfit/gadfit.F90:502-511).  enabled=True makes fit() follow
+    gadf_fit (gadfit.F90:678-915) instead of LMsolver::fit; None = argument
+    absent."""
+    enabled: bool = False
+    uphill: int = 0
+    nielsen: bool = False
+    umnigh: bool = False
+    chi2_abs: float | None = None
+    chi2_rel: float | None = None
+    grad_chi2: float | None = None
+    cos_phi: float | None = None
+    rel_error: float | None = None
+    rel_error_global: float | None = None
+
+
+STOP_REASONS = ("iteration_limit", "lambda_incs", "chi2_abs", "chi2_rel", "grad_chi2", "cos_phi",
+                "rel_error", "rel_error_global")
+
+
 def _as_f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -149,6 +171,7 @@ class LMsolver:
         self._h = C.c_void_p()
         self._keep: list = []  # borrowed arrays must outlive fit()
         self.settings = SolverSettings()
+        self.gadf = GadfOptions()
         self._check(self._api.create(model.encode(), C.byref(self._h)))
 
     # -- plumbing ---------------------------------------------------------
@@ -231,9 +254,28 @@ class LMsolver:
             self._h, int(i_par), float(val), int(bool(active)), int(i_dataset),
             parameter_name.encode() if parameter_name else None))
 
+    def _push_gadf_options(self):
+        g = self.gadf
+        if not self._api.has_gadf:
+            if g.enabled:
+                raise NotAvailable("this library has no gadf_fit driver")
+            return
+        absent = lambda v: -1.0 if v is None else float(v)  # noqa: E731
+        opts = _capi.GadfOptions(int(g.enabled), int(g.uphill), int(g.nielsen), int(g.umnigh),
+                                 absent(g.chi2_abs), absent(g.chi2_rel), absent(g.grad_chi2),
+                                 absent(g.cos_phi), absent(g.rel_error), absent(g.rel_error_global))
+        self._check(self._api.set_gadf_options(self._h, C.byref(opts)))
+
     def fit(self, lambda_: float = 10.0):
         self._push_settings()
+        self._push_gadf_options()
         self._check(self._api.fit(self._h, float(lambda_)))
+
+    def stopReason(self) -> str:
+        """Which criterion ended the last fit (gadfit_b200_stop_reason)."""
+        out = C.c_int()
+        self._check(self._api.get_stop_reason(self._h, C.byref(out)))
+        return STOP_REASONS[out.value]
 
     def getParValue(self, i_par: int, i_dataset: int = 0) -> float:
         out = C.c_double()

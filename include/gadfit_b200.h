@@ -105,6 +105,51 @@ typedef struct gadfit_b200_trial
     int decision;
 } gadfit_b200_trial;
 
+/* The options that exist only in the Fortran driver gadf_fit
+ * (fortran/gadfit/gadfit.F90:502-511; theory doc/user_guide.tex:125-216).
+ * With enabled = 1, fit() follows gadf_fit (gadfit.F90:678-915) instead of
+ * LMsolver::fit:
+ *   - a step is accepted if (1 - beta)^uphill * new_chi2 < old_chi2, beta the
+ *     D-weighted cosine between this and the previous delta1 (:756-764);
+ *   - on acceptance lambda is divided by lambda_down, or updated by Nielsen's
+ *     gain ratio (:765-770) or by Umrigar-Nightingale (:771-783);
+ *   - on rejection lambda is raised, delta1 alone is re-solved and applied
+ *     without delta2 (:785-808; LMsolver::fit recomputes both, lm_solver.cpp:476);
+ *   - old_chi2 = min(old_chi2, new_chi2) (:823), at least one iteration runs,
+ *     and after every iteration the convergence tests below are applied in
+ *     this order (:832-909); a negative tolerance means "argument absent".
+ * settings.iteration_limit is max_iter, lambda_incs / lambda_up / lambda_down /
+ * damp_max / DTD_min / acceleration_threshold keep their meaning (the Fortran
+ * defaults lambda = 1, lam_incs = 2 are the caller's to pass).  Error models
+ * (gadf_set_errors, :445-470) are sigma arrays: SQRT_Y sqrt(y), PROPTO_Y y,
+ * INVERSE_Y 1/y, USER as given. */
+typedef struct gadfit_b200_gadf_options
+{
+    int enabled;
+    int uphill;  /* exponent b; 0 = no uphill steps */
+    int nielsen; /* 1 = on */
+    int umnigh;  /* 1 = on */
+    double chi2_abs;         /* stop if chi2/dof < chi2_abs */
+    double chi2_rel;         /* stop if the relative decrease of chi2 < chi2_rel */
+    double grad_chi2;        /* stop if 2 |J^T r| < grad_chi2 */
+    double cos_phi;          /* stop if |cos(r, J delta1)| < cos_phi */
+    double rel_error;        /* stop if all |delta1 / parameter| <= rel_error */
+    double rel_error_global; /* the same over the global parameters only */
+} gadfit_b200_gadf_options;
+
+/* Why the last fit() ended */
+typedef enum gadfit_b200_stop_reason
+{
+    GADFIT_B200_STOP_ITERATION_LIMIT = 0, /* lm_solver.cpp:496 / gadfit.F90:904-908 */
+    GADFIT_B200_STOP_LAMBDA_INCS = 1,     /* lm_solver.cpp:482-494 / gadfit.F90:809-816 */
+    GADFIT_B200_STOP_CHI2_ABS = 2,        /* gadfit.F90:832-837 */
+    GADFIT_B200_STOP_CHI2_REL = 3,        /* :838-844 */
+    GADFIT_B200_STOP_GRAD_CHI2 = 4,       /* :845-857 */
+    GADFIT_B200_STOP_COS_PHI = 5,         /* :858-881 */
+    GADFIT_B200_STOP_REL_ERROR = 6,       /* :882-894 */
+    GADFIT_B200_STOP_REL_ERROR_GLOBAL = 7 /* :895-903 */
+} gadfit_b200_stop_reason;
+
 /* The five phase timers of the reference (lm_solver.h:140-144, table printed
  * by lm_solver.cpp:656-680): seconds of device time (CUDA events) and number
  * of calls, in the order Jacobian, chi2, linear algebra, omega, main loop. */
@@ -161,8 +206,17 @@ GADFIT_B200_API int gadfit_b200_default_settings(gadfit_b200_settings* out);
 GADFIT_B200_API int gadfit_b200_set_settings(gadfit_b200_solver* solver,
                              const gadfit_b200_settings* settings);
 
-/* LMsolver::fit(lambda = 10), lm_solver.h:181, lm_solver.cpp:401-511 */
+/* The Fortran-only arguments of gadf_fit (see gadfit_b200_gadf_options);
+ * default: disabled, every tolerance absent */
+GADFIT_B200_API int gadfit_b200_default_gadf_options(gadfit_b200_gadf_options* out);
+GADFIT_B200_API int gadfit_b200_set_gadf_options(gadfit_b200_solver* solver,
+                                 const gadfit_b200_gadf_options* options);
+
+/* LMsolver::fit(lambda = 10), lm_solver.h:181, lm_solver.cpp:401-511; with
+ * gadf options enabled: gadf_fit, fortran/gadfit/gadfit.F90:502-915 */
 GADFIT_B200_API int gadfit_b200_fit(gadfit_b200_solver* solver, double lambda);
+/* Which criterion ended the last fit() (gadfit_b200_stop_reason) */
+GADFIT_B200_API int gadfit_b200_get_stop_reason(gadfit_b200_solver* solver, int* out);
 
 /* getParValue / getValue / chi2 / degreesOfFreedom,
  * lm_solver.h:182-187,195, lm_solver.cpp:513-534,688-696 */

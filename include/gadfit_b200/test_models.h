@@ -210,6 +210,37 @@ using DirectIntegral13 = DirectIntegral<12, 1, 0, 1, 1>; // :1313-1344
 using DirectIntegral14 = DirectIntegral<13, 2, 1, 0, 1>; // :1345-1376
 using DirectIntegral15 = DirectIntegral<14, 1, 1, 1, 0>; // :1377-1408
 
+// The fitting functions of the reference's Fortran tests
+// (fortran/tests/1_gaussian.F90:29-33, 2_integral_single.F90:27-46); they pin
+// the gadf_fit driver (gadfit_b200_gadf_options) on the Fortran version's own
+// known answers.
+struct FortranGaussian // [fmax, x0, a, bgr]
+{
+    static constexpr int n_pars { 4 };
+    static constexpr const char* name { "fortran_gaussian" };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto u { (x - par<1>(c)) / par<2>(c) };
+        return par<0>(c) * exp(-(u * u)) + par<3>(c);
+    }
+};
+struct FortranIntegralSingle // [a, b]:  pi int_0^x t^a e^{-b t^2} dt
+{
+    static constexpr int n_pars { 2 };
+    static constexpr const char* name { "fortran_integral_single" };
+    static constexpr double pi { 3.14159265358979323846264338327950 };
+    static constexpr double rel_error { 1e-12 }; // gadf_init(f, rel_error=1e-12_kp), :57
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto integrand { [](const auto& cc, const auto& t) {
+            return pow(t, par<0>(cc)) * exp(-par<1>(cc) * (t * t));
+        } };
+        return pi * c.integrate(0.0, x, integrand, rel_error);
+    }
+};
+
 using TestModels = std::tuple<NestedIntegral1,
                               NestedIntegral2,
                               NestedIntegral3,
@@ -236,7 +267,9 @@ using TestModels = std::tuple<NestedIntegral1,
                               DirectIntegral12,
                               DirectIntegral13,
                               DirectIntegral14,
-                              DirectIntegral15>;
+                              DirectIntegral15,
+                              FortranGaussian,
+                              FortranIntegralSingle>;
 constexpr int n_test_models { static_cast<int>(std::tuple_size_v<TestModels>) };
 
 template <class F, int... I>

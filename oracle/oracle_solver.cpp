@@ -642,10 +642,9 @@ struct OracleSolver
         }
     }
 
-    // lm_solver.cpp:401-511
-    void fit(double lambda)
+    // work arrays and initial damping matrix (lm_solver.cpp:411-428)
+    void prepareWorkArrays()
     {
-        prepareIndexing();
         const int S { static_cast<int>(sets.size()) };
         std::fill(std::begin(seconds), std::end(seconds), 0.0);
         std::fill(std::begin(calls), std::end(calls), 0);
@@ -689,6 +688,18 @@ struct OracleSolver
                 DTD[c] = DTD_min[c];
             }
         }
+    }
+
+    // lm_solver.cpp:401-511
+    void fit(double lambda)
+    {
+        if (gadf.enabled != 0) {
+            fitGadf(lambda);
+            return;
+        }
+        prepareIndexing();
+        prepareWorkArrays();
+        lambda_exhausted = false;
         std::vector<std::vector<FVar>> old_parameters;
         trace.clear();
         const double t_main { omp_get_wtime() };
@@ -720,6 +731,7 @@ struct OracleSolver
                     pars = old_parameters;
                     --i_iteration;
                     finished = true;
+                    lambda_exhausted = true;
                 }
             }
             if (i_iteration == settings.iteration_limit) {
@@ -729,6 +741,217 @@ struct OracleSolver
         seconds[4] = omp_get_wtime() - t_main;
         calls[4] = 1;
         n_iterations = i_iteration;
+        stop_reason = lambda_exhausted ? GADFIT_B200_STOP_LAMBDA_INCS
+                                       : GADFIT_B200_STOP_ITERATION_LIMIT;
+    }
+
+    // ---- the Fortran driver, fortran/gadfit/gadfit.F90:678-915 ------------
+    gadfit_b200_gadf_options gadf { 0, 0, 0, 0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0 };
+    double umnigh_a { 0.5 }; // gadfit.F90:515 (a saved variable)
+    int stop_reason { 0 };
+    bool lambda_exhausted { false };
+
+    double dotD(const std::vector<double>& a, const std::vector<double>& b) const
+    {
+        double sum { 0.0 };
+        for (long long c = 0; c < n_active; ++c) {
+            sum += a[c] * (DTD[c] * b[c]);
+        }
+        return sum;
+    }
+
+    void updateDelta1Only()
+    {
+        for (size_t s = 0; s < sets.size(); ++s) {
+            size_t a { 0 };
+            for (const int k : active[s]) {
+                pars[s][k].val += delta1[column[s][a++]];
+            }
+        }
+    }
+
+    void fitGadf(double lambda)
+    {
+        if (settings.loss != 0) {
+            throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "gadf_fit has no loss functions" };
+        }
+        prepareIndexing();
+        prepareWorkArrays();
+        const int S { static_cast<int>(sets.size()) };
+        const double umnigh_m { std::exp(-0.2) }; // :516
+        std::vector<double> old_delta1(n_active, 0.0);
+        std::vector<std::vector<FVar>> old_parameters { pars };
+        trace.clear();
+        const double t_main { omp_get_wtime() };
+        double old_chi2 { chi2() };
+        double old_old_chi2 { old_chi2 };
+        int iterations { 0 };
+        stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
+        bool done { false };
+        while (!done) {
+            // STEP 1-3 (:680-743): Jacobian, JTJ, DTD rule, delta1, omega, delta2
+            computeLeftAndRightHandSide();
+            computeDeltas(lambda);
+            updateParameters(); // val + delta1 + 0.5 delta2_F, delta2_F = -delta2 (:744-750)
+            // STEP 4 (:751-818)
+            double new_chi2 { 0.0 };
+            double beta { 0.0 };
+            for (int i = 1; i <= settings.lambda_incs + 1; ++i) {
+                new_chi2 = chi2();
+                trace.push_back({ lambda, new_chi2, old_chi2, iterations + 1, 0 });
+                beta = iterations == 0 ? 0.0
+                                       : dotD(delta1, old_delta1) / std::sqrt(dotD(delta1, delta1))
+                                           / std::sqrt(dotD(old_delta1, old_delta1));
+                double factor { 1.0 };
+                for (int k = 0; k < gadf.uphill; ++k) {
+                    factor *= 1.0 - beta;
+                }
+                if (factor * new_chi2 < old_chi2) {
+                    if (gadf.nielsen != 0) {
+                        // rho = (old - new) / 2 / delta1^T (JTJ + lambda DTD) delta1, :766-769
+                        const auto A { denseJTJ() };
+                        double quad { 0.0 };
+                        for (long long r = 0; r < n_active; ++r) {
+                            double row { 0.0 };
+                            for (long long c = 0; c < n_active; ++c) {
+                                const double d { r == c ? lambda * DTD[c] : 0.0 };
+                                row += (A[r * n_active + c] + d) * delta1[c];
+                            }
+                            quad += delta1[r] * row;
+                        }
+                        const double rho { (old_chi2 - new_chi2) / 2 / quad };
+                        const double t { 2 * rho - 1 };
+                        lambda *= std::max(1 / settings.lambda_down, 1 - t * t * t);
+                    }
+                    if (gadf.umnigh != 0) { // :771-783
+                        if (new_chi2 < old_chi2 && beta >= 0.0) {
+                            umnigh_a = umnigh_a * umnigh_m + 1.0 - umnigh_m;
+                            const double t { 1.0 - std::abs(2.0 * umnigh_a - 1.0) };
+                            lambda *= std::min(1.0, std::max(1e-2, t * t));
+                        } else {
+                            umnigh_a = umnigh_a * umnigh_m + (1.0 - umnigh_m) / 2.0;
+                            if (new_chi2 >= old_chi2) {
+                                lambda /= std::min(
+                                  10.0, std::max(1.0, 1.0 - std::abs(2.0 * umnigh_a - 1.0)));
+                            }
+                        }
+                    }
+                    if (gadf.nielsen == 0 && gadf.umnigh == 0) {
+                        lambda /= settings.lambda_down;
+                    }
+                    break;
+                }
+                if (i <= settings.lambda_incs) { // :790-808
+                    trace.back().decision = 1;
+                    if (gadf.umnigh != 0) {
+                        umnigh_a *= umnigh_m;
+                        const double t { 1.0 - std::abs(2.0 * umnigh_a - 1.0) };
+                        lambda *= beta < 0.0 ? std::min(1.0, std::max(1e-2, t * t))
+                                             : std::min(1.0, std::max(0.1, t));
+                    } else {
+                        lambda = settings.lambda_up * lambda;
+                    }
+                    pars = old_parameters;
+                    factorise(lambda);
+                    delta1 = right_side;
+                    solve(delta1);
+                    updateDelta1Only();
+                } else { // :809-816
+                    trace.back().decision = 2;
+                    pars = old_parameters;
+                    stop_reason = GADFIT_B200_STOP_LAMBDA_INCS;
+                    done = true;
+                }
+            }
+            if (done) {
+                break;
+            }
+            // :819-824
+            old_parameters = pars;
+            old_delta1 = delta1;
+            old_old_chi2 = old_chi2;
+            old_chi2 = std::min(old_chi2, new_chi2);
+            ++iterations;
+            // STEP 5 (:832-909)
+            if (gadf.chi2_abs >= 0.0 && old_chi2 / dof < gadf.chi2_abs) {
+                stop_reason = GADFIT_B200_STOP_CHI2_ABS;
+                break;
+            }
+            if (gadf.chi2_rel >= 0.0 && (old_old_chi2 - old_chi2) / old_chi2 < gadf.chi2_rel) {
+                stop_reason = GADFIT_B200_STOP_CHI2_REL;
+                break;
+            }
+            if (gadf.grad_chi2 >= 0.0) {
+                double norm2 { 0.0 };
+                for (long long c = 0; c < n_active; ++c) {
+                    norm2 += right_side[c] * right_side[c];
+                }
+                if (2 * std::sqrt(norm2) < gadf.grad_chi2) {
+                    stop_reason = GADFIT_B200_STOP_GRAD_CHI2;
+                    break;
+                }
+            }
+            if (gadf.cos_phi >= 0.0) {
+                double res_Jd { 0.0 };
+                double res_res { 0.0 };
+                double Jd_Jd { 0.0 };
+                for (int s = 0; s < S; ++s) {
+                    const auto& cols { column[s] };
+                    for (int p = 0; p < sets[s].n; ++p) {
+                        const long long row { set_begin[s] + p };
+                        double Jd { 0.0 };
+                        for (size_t a = 0; a < cols.size(); ++a) {
+                            Jd += jac[row * row_stride + a] * delta1[cols[a]];
+                        }
+                        res_Jd += residuals[row] * Jd;
+                        res_res += residuals[row] * residuals[row];
+                        Jd_Jd += Jd * Jd;
+                    }
+                }
+                if (std::abs(res_Jd) / std::sqrt(res_res) / std::sqrt(Jd_Jd) < gadf.cos_phi) {
+                    stop_reason = GADFIT_B200_STOP_COS_PHI;
+                    break;
+                }
+            }
+            if (gadf.rel_error >= 0.0) {
+                bool any_large { false };
+                for (int s = 0; s < S; ++s) {
+                    size_t a { 0 };
+                    for (const int k : active[s]) {
+                        any_large = any_large
+                                    || std::abs(delta1[column[s][a++]] / pars[s][k].val)
+                                         > gadf.rel_error;
+                    }
+                }
+                if (!any_large) {
+                    stop_reason = GADFIT_B200_STOP_REL_ERROR;
+                    break;
+                }
+            }
+            if (gadf.rel_error_global >= 0.0) {
+                bool any_large { false };
+                size_t a { 0 };
+                for (const int k : active[0]) {
+                    if (global.count(k) != 0) {
+                        any_large = any_large
+                                    || std::abs(delta1[column[0][a]] / pars[0][k].val)
+                                         > gadf.rel_error_global;
+                    }
+                    ++a;
+                }
+                if (!any_large) {
+                    stop_reason = GADFIT_B200_STOP_REL_ERROR_GLOBAL;
+                    break;
+                }
+            }
+            if (iterations >= settings.iteration_limit) {
+                stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
+                break;
+            }
+        }
+        seconds[4] = omp_get_wtime() - t_main;
+        calls[4] = 1;
+        n_iterations = iterations;
     }
 };
 
@@ -815,6 +1038,23 @@ int gadfit_oracle_set_mode(OracleSolver* h, int mode)
 {
     h->mode = mode & 3;
     h->extended = (mode & 4) != 0;
+    return GADFIT_B200_OK;
+}
+
+int gadfit_oracle_default_gadf_options(gadfit_b200_gadf_options* out)
+{
+    *out = { 0, 0, 0, 0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0 };
+    return GADFIT_B200_OK;
+}
+
+int gadfit_oracle_set_gadf_options(OracleSolver* h, const gadfit_b200_gadf_options* o)
+{
+    return guarded(h, [&] { h->gadf = *o; });
+}
+
+int gadfit_oracle_get_stop_reason(OracleSolver* h, int* out)
+{
+    *out = h->stop_reason;
     return GADFIT_B200_OK;
 }
 
