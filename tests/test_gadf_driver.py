@@ -178,27 +178,29 @@ def test_device_option_paths_match_oracle(case, fx):
 
 
 @pytest.mark.gpu
-def test_device_gadf_driver_with_local_blocks_matches_oracle():
-    """Block-arrow path (shared + local parameters in many data sets), with
-    tolerances that need the reduced scalars of every local block."""
+@pytest.mark.parametrize("opts,limit", [(dict(uphill=1, rel_error=1e-6, chi2_rel=1e-9), 30),
+                                        (dict(nielsen=True, rel_error=1e-7), 12)],
+                         ids=["uphill_chi2_rel", "nielsen"])
+def test_device_gadf_driver_with_local_blocks_matches_oracle(opts, limit):
+    """Block-arrow path (shared + local parameters in many data sets): the
+    reduced scalars need the contribution of every local block."""
     from gadfit_b200 import workloads as W
     recs = []
     for make in (backends.product_solver(), backends.oracle_solver(1)):
         w = W.WORKLOADS["C3"](n_sets=12, n_points=300)
         s = make(w.model)
         w.setup(s)
-        s.gadf = g.GadfOptions(enabled=True, uphill=1, rel_error=1e-7, cos_phi=1e-9)
-        s.settings.iteration_limit = 30
+        s.gadf = g.GadfOptions(enabled=True, **opts)
+        s.settings.iteration_limit = limit
         s.settings.lambda_incs = 2
         s.settings.acceleration_threshold = 0.9
         s.fit(1.0)
         recs.append(dict(pars=[s.getParValue(k, d) for d in range(w.n_sets) for k in range(w.n_pars)],
                          chi2=s.chi2(), stop=s.stopReason(), it=s.iterations(),
-                         dec=[t["decision"] for t in s.trace()]))
+                         dec=[t["decision"] for t in s.trace()], lam=[t["lambda_"] for t in s.trace()]))
     got, want = recs
     assert got["stop"] == want["stop"] and got["it"] == want["it"] and got["dec"] == want["dec"]
-    # 30 iterations with uphill steps; the weakest-determined parameter (a
-    # background slope) moves by 1e-9 relative from summation order alone
+    np.testing.assert_allclose(got["lam"], want["lam"], rtol=1e-8)
     np.testing.assert_allclose(got["pars"], want["pars"], rtol=1e-8, atol=1e-11)
     np.testing.assert_allclose(got["chi2"], want["chi2"], rtol=1e-10)
 
