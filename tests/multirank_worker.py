@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import backends  # noqa: E402
-from gadfit_b200 import LMsolver, comm_unique_id, partition  # noqa: E402
+from gadfit_b200 import GadfOptions, LMsolver, comm_unique_id, partition  # noqa: E402
 from gadfit_b200 import workloads as W  # noqa: E402
 
 
@@ -26,10 +26,13 @@ def main():
     ids = [comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     report = {}
-    cases = [("C3", dict(n_sets=37, n_points=400)),      # whole data sets per rank
-             ("C4", dict(n_sets=9, n_points=300)),       # + geodesic acceleration
-             ("C2", dict(n_sets=1, n_points=50_000))]    # fewer sets than ranks: point split
-    for i, (name, kw) in enumerate(cases):
+    cases = [("C3", dict(n_sets=37, n_points=400), None),    # whole data sets per rank
+             ("C4", dict(n_sets=9, n_points=300), None),     # + geodesic acceleration
+             ("C2", dict(n_sets=1, n_points=50_000), None),  # fewer sets than ranks: point split
+             # the Fortran driver: its reduced scalars are all-reduced too
+             ("C3", dict(n_sets=12, n_points=300), dict(nielsen=True, rel_error=1e-7)),
+             ("C2", dict(n_sets=1, n_points=20_000), dict(chi2_rel=1e-6, grad_chi2=1e-3))]
+    for i, (name, kw, gadf) in enumerate(cases):
         w = W.WORKLOADS[name](**kw)
         first, end, split = partition([w.n_points] * w.n_sets, rank, world)
         s = LMsolver(w.model)
@@ -39,6 +42,9 @@ def main():
         s.setComm(rank, world, ids[0])
         # each rank only hands over the data sets it owns (all of them when split)
         w.setup(s, owned=None if split else range(first, end))
+        if gadf is not None:
+            s.gadf = GadfOptions(enabled=True, **gadf)
+            s.settings.iteration_limit = 12
         s.fit(w.lambda0)
         got = dict(chi2=s.chi2(), pars=[[s.getParValue(k, j) for k in range(w.n_pars)]
                                         for j in range(w.n_sets)],
@@ -48,11 +54,15 @@ def main():
             o = backends.oracle_solver(2)(w.model)
             w.setup(o)
             o.settings.n_threads = 4
+            if gadf is not None:
+                o.gadf = GadfOptions(enabled=True, **gadf)
+                o.settings.iteration_limit = 12
             o.fit(w.lambda0)
             want = dict(chi2=o.chi2(), pars=[[o.getParValue(k, j) for k in range(w.n_pars)]
                                              for j in range(w.n_sets)],
                         decisions=[t["decision"] for t in o.trace()], iterations=o.iterations())
-            report[name] = dict(got=got, want=want, split=split)
+            got["stop"], want["stop"] = s.stopReason(), o.stopReason()
+            report[name if gadf is None else name + "_gadf"] = dict(got=got, want=want, split=split)
         # all ranks must hold the same parameters after the fit
         t = torch.tensor(got["pars"], dtype=torch.float64)
         ref = t.clone()

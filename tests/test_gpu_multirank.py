@@ -37,7 +37,9 @@ def test_two_ranks_reproduce_the_single_process_oracle(tmp_path):
         assert got["comm"]["peer_reductions"] > 0
         n = min(len(got["decisions"]), len(want["decisions"]), 6)
         assert got["decisions"][:n] == want["decisions"][:n], name
-        np.testing.assert_allclose(got["chi2"], want["chi2"], rtol=1e-10)
+        np.testing.assert_allclose(got["chi2"], want["chi2"], rtol=1e-10, err_msg=name)
         gp, wp = np.array(got["pars"]), np.array(want["pars"])
         floor = 1e-9 * np.max(np.abs(wp), axis=0, keepdims=True)
         assert np.all(np.abs(gp - wp) <= 1e-8 * np.abs(wp) + floor), name
+        if name.endswith("_gadf"):  # the Fortran driver: same stop criterion on every path
+            assert got["stop"] == want["stop"] and got["iterations"] == want["iterations"], name
