@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libgadfit_b200.so")
 N_MODEL_GROUPS = 3  # models::n_model_groups in include/gadfit_b200/fit_models.h
-N_TEST_MODELS = 29  # models::n_test_models in include/gadfit_b200/test_models.h
+N_TEST_MODELS = 30  # models::n_test_models in include/gadfit_b200/test_models.h
 TEST_MODELS_OUT = os.path.join(HERE, "libgadfit_b200_testmodels.so")
 
 NVCC_FLAGS = [

@@ -157,6 +157,42 @@ GADFIT_HD auto par(const Ctx& c)
     return c.template get<K>();
 }
 
+// Semi-infinite integration ranges, as in the Fortran version
+// (fortran/gadfit/numerical_integration.F90:286-352): the integral over
+// (lower, +inf) is mapped to (0, 1] by x = lower + (1 - t)/t, the one over
+// (-inf, upper) by x = upper - (1 - t)/t, and the adaptive rule is applied to
+// the transformed integrand f(x)/t^2.  Written against the context interface
+// only, so the same code serves the device contexts, the reference's AdVar
+// and the oracle's dual.
+template <class Ctx, class F>
+GADFIT_HD auto integrate_to_infinity(const Ctx& c,
+                                     const double lower,
+                                     F&& f,
+                                     const double rel_error,
+                                     const double abs_error = 0.0)
+{
+    return c.integrate(
+      0.0,
+      1.0,
+      [&f, lower](const auto& cc, const auto& t) { return f(cc, lower - 1 + 1 / t) / (t * t); },
+      rel_error,
+      abs_error);
+}
+template <class Ctx, class F>
+GADFIT_HD auto integrate_from_minus_infinity(const Ctx& c,
+                                             const double upper,
+                                             F&& f,
+                                             const double rel_error,
+                                             const double abs_error = 0.0)
+{
+    return c.integrate(
+      0.0,
+      1.0,
+      [&f, upper](const auto& cc, const auto& t) { return f(cc, upper + 1 - 1 / t) / (t * t); },
+      rel_error,
+      abs_error);
+}
+
 // Value of any AD type
 GADFIT_HD double value_of(const double x)
 {

@@ -240,6 +240,28 @@ struct FortranIntegralSingle // [a, b]:  pi int_0^x t^a e^{-b t^2} dt
         return pi * c.integrate(0.0, x, integrand, rel_error);
     }
 };
+// fortran/tests/3_integral_double.F90:27-61, [a, b]:
+//   f(x) = 1/x int_0^inf e^{-t} [ int_0^{x/b} log((e^u - 1) q(t) + 1)/u du ] dt,
+//   q(t) = 1 + b a erf(t);  gadf_init(rel_error_inner=1e-6, rel_error=1e-5), :75-76
+struct FortranIntegralDouble
+{
+    static constexpr int n_pars { 2 };
+    static constexpr const char* name { "fortran_integral_double" };
+    static constexpr double rel_error_inner { 1e-6 };
+    static constexpr double rel_error_outer { 1e-5 };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        const auto outer { [x](const auto& co, const auto& t) {
+            const auto inner { [&t](const auto& ci, const auto& u) {
+                const auto q { 1 + par<1>(ci) * par<0>(ci) * erf(t) };
+                return log((exp(u) - 1.0) * q + 1.0) / u;
+            } };
+            return exp(-t) * co.integrate(0.0, x / par<1>(co), inner, rel_error_inner);
+        } };
+        return integrate_to_infinity(c, 0.0, outer, rel_error_outer) / x;
+    }
+};
 
 using TestModels = std::tuple<NestedIntegral1,
                               NestedIntegral2,
@@ -269,7 +291,8 @@ using TestModels = std::tuple<NestedIntegral1,
                               DirectIntegral14,
                               DirectIntegral15,
                               FortranGaussian,
-                              FortranIntegralSingle>;
+                              FortranIntegralSingle,
+                              FortranIntegralDouble>;
 constexpr int n_test_models { static_cast<int>(std::tuple_size_v<TestModels>) };
 
 template <class F, int... I>

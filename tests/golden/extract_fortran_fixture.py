@@ -1,5 +1,5 @@
 """Extract the data arrays of the reference's Fortran tests
-(reference fortran/tests/{1_gaussian,2_integral_single,4_multiple_curves}_data.F90)
+(reference fortran/tests/{1_gaussian,2_integral_single,3_integral_double,4_multiple_curves}_data.F90)
 into tests/golden/fortran_fixture.json.
 
 Run in the build container, where /root/reference is mounted:
@@ -27,7 +27,7 @@ def arrays(path: str) -> dict:
 if __name__ == "__main__":
     out = {}
     for stem, prefix in (("1_gaussian", "gaussian"), ("2_integral_single", "integral_single"),
-                         ("4_multiple_curves", "multiple_curves")):
+                         ("3_integral_double", "integral_double"), ("4_multiple_curves", "multiple_curves")):
         for name, values in arrays(os.path.join(SRC, stem + "_data.F90")).items():
             out[f"{prefix}_{name}"] = values
     out["_source"] = "reference fortran/tests/*_data.F90"

@@ -5,7 +5,7 @@ after a rejection, and the convergence tests.
 
 Pinned on the known answers of the reference's own Fortran tests
 (fortran/tests/4_multiple_curves.F90:55-61, 1_gaussian.F90:65,
-2_integral_single.F90:74) -- the Fortran sources cannot be compiled here (no
+2_integral_single.F90:74, 3_integral_double.F90:96 -- all four) -- the Fortran sources cannot be compiled here (no
 gfortran), so these literals are the pin.  They exercise the driver with
 acceleration, error models and max_iter; the option paths they do not reach
 (rejections, uphill, nielsen, umnigh, tolerances) are restated from the
@@ -94,6 +94,22 @@ def run_integral_single(make, fx):
     return s
 
 
+def run_integral_double(make, fx):
+    """3_integral_double.F90:75-89: nested integral, outer range (0, inf), USER errors."""
+    s = make("fortran_integral_double")
+    x, y, e = (fx["integral_double_" + k] for k in ("x_data", "y_data", "weights"))
+    s._keep = [x, y, e]
+    s.addDataset(x, y, e)
+    s.setPar(0, 1.0, True)
+    s.setPar(1, 1.0, True)
+    s.gadf = g.GadfOptions(enabled=True)
+    s.settings.iteration_limit = 3
+    s.settings.lambda_incs = 2
+    s.settings.acceleration_threshold = F32(0.9)
+    s.fit(F32(0.1))
+    return s
+
+
 def check_fortran_known_answers(make, fx, slack):
     """slack multiplies the tolerances the Fortran tests use themselves."""
     s = run_multiple_curves(make, fx)
@@ -104,6 +120,8 @@ def check_fortran_known_answers(make, fx, slack):
     np.testing.assert_allclose(s.getParValue(2), 33.416146356055293, rtol=0, atol=1e-13 * slack)
     s = run_integral_single(make, fx)
     np.testing.assert_allclose(s.getParValue(0), 7.5549166396989014, rtol=0, atol=1e-11 * slack)
+    s = run_integral_double(make, fx)
+    np.testing.assert_allclose(s.getParValue(0), 8.5799477799920343, rtol=0, atol=1e-9 * slack)
 
 
 def test_oracle_reproduces_the_fortran_known_answers(fx):
