@@ -46,6 +46,10 @@ class Trial(C.Structure):
     ]
 
 
+# gadfit_b200_log_fn
+LOG_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
+
+
 class GadfOptions(C.Structure):
     """gadfit_b200_gadf_options: the Fortran-only arguments of gadf_fit"""
     _fields_ = [
@@ -92,7 +96,7 @@ CORE_SYMBOLS = [
     "get_trace", "n_iterations", "get_timings", "last_error",
 ]
 PRODUCT_ONLY_SYMBOLS = [
-    "default_gadf_options", "set_gadf_options", "get_stop_reason",
+    "default_gadf_options", "set_gadf_options", "get_stop_reason", "set_log",
     "n_models", "model_info", "load_models", "n_launches", "jacobian_kernel_time",
     "status_name", "set_device", "upload", "comm_unique_id", "set_comm",
     "partition", "measure_fp64_peak", "microbench", "comm_stats",
@@ -132,6 +136,9 @@ class Api:
             "get_timings": ([vp, C.POINTER(Timings)], C.c_int),
             "last_error": ([vp], C.c_char_p),
         }
+        self.has_ref_log = prefix == "gadfit_ref_"
+        if self.has_ref_log:
+            sig["get_log"] = ([vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)], C.c_int)
         self.has_gadf = product or prefix == "gadfit_oracle_"
         if self.has_gadf:
             sig.update({
@@ -141,6 +148,7 @@ class Api:
             })
         if product:
             sig.update({
+                "set_log": ([vp, LOG_FN, vp], C.c_int),
                 "n_models": ([], C.c_int),
                 "model_info": ([C.c_int, C.POINTER(C.c_char_p), c_int_p], C.c_int),
                 "load_models": ([C.c_char_p], C.c_int),

@@ -14,7 +14,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <charconv>
+#include <cstdio>
 #include <cstring>
+#include <iomanip>
+#include <limits>
+#include <sstream>
 #include <dlfcn.h>
 #include <mutex>
 #include <string_view>
@@ -227,6 +232,9 @@ struct SolverImpl
     bool fitted { false };
     double lambda_lhs { 0.0 };      // lambda of the last left-hand side
     bool have_delta2 { false };
+    // text output of the reference (printIterationResults / printTimings)
+    gadfit_b200_log_fn log_fn { nullptr };
+    void* log_user { nullptr };
     // the Fortran driver (gadfit_b200_gadf_options)
     gadfit_b200_gadf_options gadf { 0, 0, 0, 0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0 };
     double umnigh_a { 0.5 }; // gadfit.F90:515, a saved variable: persists across fits
@@ -955,6 +963,150 @@ struct SolverImpl
         }
     }
 
+    // ---- text output, lm_solver.cpp:587-686 ---------------------------------
+    // Emitted line by line to the sink installed with gadfit_b200_set_log (the
+    // library itself never writes to stdout); which lines appear is decided
+    // by settings.verbosity exactly as in the reference.
+    enum : unsigned
+    {
+        io_all = 1U,
+        io_delta1 = 2U,
+        io_delta2 = 4U,
+        io_timings = 8U,
+        io_hide_local = 16U,
+        io_hide_global = 32U,
+        io_hide_all = 64U,
+        io_final_only = 128U
+    };
+    [[nodiscard]] auto io_test(const unsigned flag) const -> bool // lm_solver.cpp:682-686
+    {
+        return (settings.verbosity & io_all) != 0U || (settings.verbosity & flag) != 0U;
+    }
+    auto log_line(const std::string& line) const -> void
+    {
+        if (log_fn != nullptr) {
+            log_fn(line.c_str(), log_user);
+        }
+    }
+    // "{}" of a double in the reference's spdlog/fmt: shortest round-trip form
+    static auto shortest(const double v) -> std::string
+    {
+        char buf[40];
+        const auto res { std::to_chars(buf, buf + sizeof(buf), v) };
+        return std::string { buf, res.ptr };
+    }
+    // delta1 / delta2 as dense vectors over the Jacobian columns
+    auto dense_delta(const bool second) -> std::vector<double>
+    {
+        std::vector<double> out(static_cast<size_t>(n_active), 0.0);
+        const int S { static_cast<int>(sets.size()) };
+        if (world > 1 && !part.split) {
+            return out; // remote local blocks are not gathered for printing
+        }
+        const auto d { download(second ? d_delta2_par.ptr : d_delta1_par.ptr,
+                                static_cast<size_t>(S) * NP) };
+        for (int set = 0; set < S; ++set) {
+            for (int k = 0; k < NP; ++k) {
+                const long long c { column(set, k) };
+                if (c >= 0) {
+                    out[c] = d[static_cast<size_t>(set) * NP + k];
+                }
+            }
+        }
+        return out;
+    }
+    // printIterationResults, lm_solver.cpp:587-654
+    auto print_iteration_results(const int i_iteration, const double lambda, const double chi2)
+      -> void
+    {
+        if (log_fn == nullptr) {
+            return;
+        }
+        download_parameters();
+        const bool show_d1 { io_test(io_delta1) };
+        const bool show_d2 { io_test(io_delta2) && have_delta2 };
+        const auto delta1 { show_d1 ? dense_delta(false) : std::vector<double> {} };
+        auto delta2 { show_d2 ? dense_delta(true) : std::vector<double> {} };
+        if (show_d2 && download(d_state.ptr, 1).front().use_delta2 == 0) {
+            std::fill(delta2.begin(), delta2.end(), 0.0); // lm_solver.cpp:394-396
+        }
+        log_line("Iteration: " + std::to_string(i_iteration));
+        log_line("Lambda: " + shortest(lambda));
+        log_line("Chi2/DOF: " + shortest(chi2 / dof));
+        const int S { static_cast<int>(sets.size()) };
+        const auto parameter_line { [&](const int i_set, const int i_par) {
+            std::ostringstream line {};
+            line << std::setprecision(std::numeric_limits<double>::digits10);
+            if (i_par < static_cast<int>(names.size()) && !names[i_par].empty()) {
+                line << std::setw(15) << names[i_par] << ": ";
+            } else {
+                line << "    Parameter " << i_par << ": ";
+            }
+            line << par[static_cast<size_t>(i_set) * NP + i_par];
+            const long long c { column(i_set, i_par) };
+            if (c >= 0) {
+                if (show_d1) {
+                    line << " (" << delta1[c] << ')';
+                }
+                if (io_test(io_delta2) && !delta2.empty()) {
+                    line << " (" << delta2[c] << ')';
+                }
+            } else {
+                line << " (fixed)";
+            }
+            log_line(line.str());
+        } };
+        const bool single_dataset { S == 1 };
+        const auto is_global { [&](const int i_par) { // Indices::global
+            return ((global_mask >> i_par) & 1U) != 0U;
+        } };
+        if (!single_dataset && !io_test(io_hide_global)) {
+            log_line("  Global parameters");
+            for (int i_par = 0; i_par < NP; ++i_par) {
+                if (is_global(i_par)) {
+                    parameter_line(0, i_par);
+                }
+            }
+        }
+        if (!io_test(io_hide_local)) {
+            for (int i_set = 0; i_set < S; ++i_set) {
+                if (S > 1) {
+                    log_line("  Data set: " + std::to_string(i_set));
+                }
+                for (int i_par = 0; i_par < NP; ++i_par) {
+                    if (single_dataset || !is_global(i_par)) {
+                        parameter_line(i_set, i_par);
+                    }
+                }
+            }
+        }
+        log_line("");
+    }
+    // printTimings, lm_solver.cpp:656-680 (device seconds in both time columns)
+    auto print_timings() -> void
+    {
+        if (log_fn == nullptr) {
+            return;
+        }
+        const auto row { [&](const char* term, const PhaseTimer& t) {
+            char buf[96];
+            std::snprintf(buf, sizeof(buf), "%-14s %10.2f %10.2f  %6.2f%% %5d", term, t.seconds,
+                          t.seconds, 100 * t.seconds / t_main.seconds, t.calls);
+            log_line(buf);
+        } };
+        log_line("");
+        log_line("Timings          Wall (s)    CPU (s)  CPU rel  Calls");
+        log_line("====================================================");
+        row("Jacobian", t_jacobian);
+        row("Chi2", t_chi2);
+        row("Linear algebra", t_linalg);
+        row("Omega", t_omega);
+        log_line("----------------------------------------------------");
+        row("Main loop", t_main);
+        log_line("====================================================");
+        log_line("");
+    }
+
     // LMsolver::fit, lm_solver.cpp:401-511
     auto fit(const double lambda0) -> void
     {
@@ -988,6 +1140,7 @@ struct SolverImpl
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
         lambda_lhs = lambda0;
         double lambda { lambda0 };
+        double last_old_chi2 { 0.0 };
 
         t_main.start(stream);
         chi2_phase(&d_state.ptr->new_chi2);
@@ -1027,19 +1180,32 @@ struct SolverImpl
                 trace.push_back(
                   { rec.lambda, rec.new_chi2, rec.old_chi2, i_iteration, rec.decision });
                 lambda = now.lambda;
+                last_old_chi2 = now.old_chi2;
+                const bool chatty { !io_test(io_hide_all) && !io_test(io_final_only) };
                 if (rec.decision == 0) {
+                    if (chatty) { // lm_solver.cpp:465-467
+                        print_iteration_results(i_iteration, lambda, rec.new_chi2);
+                    }
                     break;
                 }
                 if (rec.decision == 1) {
                     lambda_lhs = lambda;
                     solve_phase(false);
                 } else {
+                    if (chatty) { // lm_solver.cpp:484-488
+                        log_line("Lambda increased " + std::to_string(settings.lambda_incs)
+                                 + " times in a row");
+                        log_line("");
+                    }
                     --i_iteration;
                     finished = true;
                     stop_reason = GADFIT_B200_STOP_LAMBDA_INCS;
                 }
             }
             if (i_iteration == settings.iteration_limit) {
+                if (!io_test(io_hide_all)) { // lm_solver.cpp:497-499
+                    log_line("Iteration limit reached");
+                }
                 finished = true;
             }
         }
@@ -1051,6 +1217,19 @@ struct SolverImpl
             t->collect();
         }
         fitted = true;
+        // lm_solver.cpp:504-510
+        if ((!io_test(io_hide_all) && io_test(io_final_only)) || settings.iteration_limit == 0) {
+            if (settings.iteration_limit == 0 && log_fn != nullptr) {
+                GADFIT_CUDA_TRY(cudaMemcpyAsync(h_mirror, d_state.ptr, sizeof(LmState),
+                                                cudaMemcpyDeviceToHost, stream));
+                GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+                last_old_chi2 = h_mirror[0].old_chi2;
+            }
+            print_iteration_results(i_iteration, lambda, last_old_chi2);
+        }
+        if (!io_test(io_hide_all) && io_test(io_timings)) {
+            print_timings();
+        }
     }
 
     // gadf_fit, fortran/gadfit/gadfit.F90:678-915: the same sweeps and solves,
@@ -1811,6 +1990,14 @@ int gadfit_b200_set_settings(gadfit_b200_solver* solver, const gadfit_b200_setti
             solver->DTD_min = { 0.0 };
         }
         solver->settings.DTD_min = nullptr;
+    });
+}
+
+int gadfit_b200_set_log(gadfit_b200_solver* solver, gadfit_b200_log_fn fn, void* user)
+{
+    return guarded(solver, [&] {
+        solver->log_fn = fn;
+        solver->log_user = user;
     });
 }
 

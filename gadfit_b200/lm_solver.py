@@ -266,6 +266,28 @@ class LMsolver:
                                  absent(g.cos_phi), absent(g.rel_error), absent(g.rel_error_global))
         self._check(self._api.set_gadf_options(self._h, C.byref(opts)))
 
+    def setLog(self, sink) -> None:
+        """Text output of the reference's fit() -- iteration results, timing
+        table, termination messages (lm_solver.cpp:485,498,587-680) -- one call
+        of sink(line) per line, selected by settings.verbosity as in the
+        reference.  None removes the sink (the default: nothing is printed)."""
+        if not self._api.product:
+            raise NotAvailable("setLog is a product entry point (the reference logs via spdlog)")
+        if sink is None:
+            self._log_cb = None
+            self._check(self._api.set_log(self._h, _capi.LOG_FN(0), None))
+            return
+        self._log_cb = _capi.LOG_FN(lambda line, _user: sink(line.decode()))
+        self._check(self._api.set_log(self._h, self._log_cb, None))
+
+    def referenceLog(self) -> list[str]:
+        """(compiled reference only) its own info-level output of the last fit"""
+        need = C.c_size_t()
+        self._check(self._api.get_log(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self._check(self._api.get_log(self._h, buf, need.value, C.byref(need)))
+        return buf.value.decode().split("\n")[:-1]
+
     def fit(self, lambda_: float = 10.0):
         self._push_settings()
         self._push_gadf_options()

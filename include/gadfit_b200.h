@@ -206,6 +206,20 @@ GADFIT_B200_API int gadfit_b200_default_settings(gadfit_b200_settings* out);
 GADFIT_B200_API int gadfit_b200_set_settings(gadfit_b200_solver* solver,
                              const gadfit_b200_settings* settings);
 
+/* Text output of LMsolver::fit -- printIterationResults / printTimings and
+ * the termination messages, lm_solver.cpp:485,498,587-680.  The library never
+ * writes to stdout itself: with a sink installed, fit() hands it the lines the
+ * reference would log at info level (one call per line, no newline), selected
+ * by settings.verbosity exactly as in the reference (io::flag bits,
+ * lm_solver.h:60-72; 0 = results of every iteration).  Numbers are formatted
+ * like the reference's ("{}" shortest round-trip, parameter lines with 15
+ * significant digits).  Without a sink nothing is formatted or downloaded.
+ * NULL removes the sink. */
+typedef void (*gadfit_b200_log_fn)(const char* line, void* user);
+GADFIT_B200_API int gadfit_b200_set_log(gadfit_b200_solver* solver,
+                                        gadfit_b200_log_fn sink,
+                                        void* user);
+
 /* The Fortran-only arguments of gadf_fit (see gadfit_b200_gadf_options);
  * default: disabled, every tolerance absent */
 GADFIT_B200_API int gadfit_b200_default_gadf_options(gadfit_b200_gadf_options* out);

@@ -28,6 +28,7 @@
 
 #include <bitset>
 #include <cassert>
+#include <cstdio>
 #include <exception>
 #include <string>
 #include <vector>
@@ -105,6 +106,7 @@ enum class Loss
 class LMsolver
 {
 private:
+    static auto printLine(const char* line, void*) -> void { std::puts(line); }
     static constexpr int global_dataset_idx { -1 };
     gadfit_b200_solver* handle { nullptr };
     std::vector<double> buffer; // backing store of the getter that ran last
@@ -178,6 +180,15 @@ public:
     explicit LMsolver(const std::string& model_name)
     {
         check(gadfit_b200_create(model_name.c_str(), &handle));
+        // The reference logs its iteration results through spdlog by default
+        // (lm_solver.cpp:465-467,587-654, pattern "%v" in its example): same
+        // lines, to stdout, unless the caller installs another sink.
+        setLog(&LMsolver::printLine, nullptr);
+    }
+    // Where the text output of fit() goes (gadfit_b200_set_log); nullptr = nowhere
+    auto setLog(gadfit_b200_log_fn sink, void* user) -> void
+    {
+        check(gadfit_b200_set_log(handle, sink, user));
     }
     LMsolver(const LMsolver&) = delete;
     auto operator=(const LMsolver&) -> LMsolver& = delete;

@@ -27,6 +27,7 @@
 #include "gadfit_b200/fit_models.h"
 #include "gadfit_b200/test_models.h"
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <omp.h>
@@ -135,6 +136,7 @@ struct RefSolver
     int n_iterations {};
     std::vector<double> DTD_min;
     std::string last_error;
+    std::string log; // info-level text of the last fit, one line per message
 };
 
 template <class F>
@@ -259,10 +261,24 @@ int gadfit_ref_set_settings(RefSolver* h, const gadfit_b200_settings* s)
     return GADFIT_B200_OK;
 }
 
+// The reference's own info-level output of the last fit (what spdlog would
+// have printed with the pattern "%v"), lines separated by '\n'
+int gadfit_ref_get_log(RefSolver* h, char* buf, size_t cap, size_t* need)
+{
+    *need = h->log.size() + 1;
+    if (buf != nullptr && cap > 0) {
+        const size_t n { std::min(cap - 1, h->log.size()) };
+        std::memcpy(buf, h->log.data(), n);
+        buf[n] = '\0';
+    }
+    return GADFIT_B200_OK;
+}
+
 int gadfit_ref_fit(RefSolver* h, double lambda)
 {
     auto& events { spdlog::oracle_events() };
     events.clear();
+    spdlog::oracle_log().clear();
     h->solver->settings.verbosity |= gadfit::io::timings;
     const int status { guarded(h, [&] { h->solver->fit(lambda); }) };
     h->trace.clear();
@@ -272,6 +288,11 @@ int gadfit_ref_fit(RefSolver* h, double lambda)
     // Replay the reference's log (lm_solver.cpp:454-501): a trial record is
     // followed by "Iteration: N" iff it was accepted; "Lambda increased"
     // marks the last rejected trial as the give-up.
+    h->log.clear();
+    for (const auto& line : spdlog::oracle_log()) {
+        h->log += line;
+        h->log += '\n';
+    }
     for (const auto& e : events) {
         switch (e.kind) {
         case 0:

@@ -15,9 +15,13 @@
 //   info("Lambda increased {} times in a row") lm_solver.cpp:485
 //   info("Iteration limit reached")            lm_solver.cpp:498
 //
-// The records are bit-exact doubles, not parsed text.
+// The records are bit-exact doubles, not parsed text.  In addition every
+// info-level message is formatted (std::vformat has the semantics of the fmt
+// library spdlog uses) and kept as a line of text, so that the product's text
+// output can be compared with the reference's own (oracle_log).
 #pragma once
 
+#include <format>
 #include <string>
 #include <string_view>
 #include <type_traits>
@@ -43,6 +47,12 @@ inline auto oracle_events() -> std::vector<OracleEvent>&
 {
     static std::vector<OracleEvent> events {};
     return events;
+}
+
+inline auto oracle_log() -> std::vector<std::string>&
+{
+    static std::vector<std::string> lines {};
+    return lines;
 }
 
 namespace detail {
@@ -71,6 +81,7 @@ auto debug(std::string_view fmt, const Args&... args) -> void
 template <class... Args>
 auto info(std::string_view fmt, const Args&... args) -> void
 {
+    oracle_log().push_back(std::vformat(fmt, std::make_format_args(args...)));
     if constexpr (sizeof...(Args) == 1) {
         const double v[1] { detail::as_double(args)... };
         if (fmt.starts_with("Iteration: ")) {

@@ -56,6 +56,9 @@ int main(int argc, char** argv)
         }
     }
     if (argc > 1 && std::strcmp(argv[1], "fit") == 0) {
+        // iteration results go to stdout by default, as in the reference; the
+        // last fit below shows them, this one is quiet
+        solver.settings.verbosity = gadfit::io::hide_all;
         solver.settings.iteration_limit = 6;
         solver.settings.acceleration_threshold = 0.9;
         solver.fit(1.0);
@@ -68,6 +71,12 @@ int main(int argc, char** argv)
                     solver.trace().size());
         const auto& jtj { solver.getJTJ() };
         std::printf("jtj_size %zu\n", jtj.size());
+        // default verbosity: the reference's per-iteration report on stdout
+        solver.settings.verbosity = gadfit::io::final_only;
+        solver.settings.iteration_limit = 1;
+        std::printf("report_begin\n");
+        solver.fit(1.0);
+        std::printf("report_end\n");
     }
     return caught == 3 ? 0 : 1;
 }

@@ -38,7 +38,12 @@ def test_cpp_wrapper_compiles_and_enforces_call_order(exe):
 @pytest.mark.gpu
 def test_cpp_wrapper_fit_matches_oracle(exe):
     r = subprocess.run([exe, "fit"], capture_output=True, text=True, check=True)
-    got = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.splitlines()}
+    out = r.stdout.splitlines()
+    report = out[out.index("report_begin") + 1:out.index("report_end")]
+    # gadfit::LMsolver prints like the reference does by default (stdout)
+    assert report[0] == "Iteration limit reached" and report[1] == "Iteration: 1"
+    assert "  Global parameters" in report and "  Data set: 1" in report
+    got = {ln.split()[0]: ln.split()[1:] for ln in out[:out.index("report_begin")] if ln.strip()}
     x = np.arange(1.0, 9.0)
     y1 = np.array([56.0, 51.0, 54.0, 46.0, 50.0, 48.0, 31.0, 45.0])
     y2 = np.array([153.0, 157.0, 137.0, 111.0, 126.0, 108.0, 113.0, 128.0])
