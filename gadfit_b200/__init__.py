@@ -13,3 +13,4 @@ from .lm_solver import (  # noqa: F401
     UnknownModel, UnknownOperation, comm_unique_id, io, load_models,
     load_test_models, measure_fp64_peak, models, partition,
 )
+from .user_models import define_model, model_source  # noqa: F401,E402

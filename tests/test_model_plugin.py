@@ -95,3 +95,26 @@ def test_user_function_with_adaptive_integral_recovers_its_parameters(user_plugi
     assert s.chi2() < 1e-14
     np.testing.assert_allclose(s.getValue(3.0), truth[0] * quad(
         lambda t: np.exp(-(t / truth[1]) ** truth[2]), 0.0, 3.0)[0] + truth[3], rtol=1e-7)
+
+
+# ---- fitting functions defined from Python (gadfit_b200.define_model) -------
+
+def test_define_model_generates_compiles_and_registers(tmp_path):
+    src = g.model_source("py_decay", 3, "P(0) * exp(-x / P(1)) + P(2)")
+    assert "GADFIT_B200_REGISTER_MODEL(UserModel_py_decay)" in src and "return P(0)" in src
+    so = g.define_model("py_decay", 3, "P(0) * exp(-x / P(1)) + P(2)", cache_dir=str(tmp_path))
+    assert os.path.exists(so) and g.models()["py_decay"] == 3
+    with pytest.raises(g.InvalidArgument):
+        g.define_model("py_decay", 3, "P(0)", cache_dir=str(tmp_path))  # name taken
+    with pytest.raises(g.InvalidArgument):
+        g.model_source("not an identifier", 1, "P(0)")
+
+
+@pytest.mark.gpu
+def test_python_defined_function_reproduces_the_builtin_known_answers(c1, tmp_path):
+    if "py_decay_gpu" not in g.models():
+        g.define_model("py_decay_gpu", 3, "P(0) * exp(-x / P(1)) + P(2)", cache_dir=str(tmp_path))
+    sc = scenarios.C1_SCENARIOS[0]
+    builtin, _ = scenarios.run(sc, lambda _m: g.LMsolver("exponential"), c1)
+    user, _ = scenarios.run(sc, lambda _m: g.LMsolver("py_decay_gpu"), c1)
+    assert builtin["chi2"] == user["chi2"] and builtin["pars"] == user["pars"]
