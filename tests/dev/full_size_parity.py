@@ -3,7 +3,7 @@ shared parameters) fitted by the CUDA library and by the UNMODIFIED reference
 (oracle/_ref, all host threads) on identical inputs.  Writes
 gpurun_out/full_size_parity_c2.json (copied to profiles/ once produced).
 
-    gpurun -- python tools/full_size_parity.py [n_sets] [n_points] [iterations]
+    gpurun -- python tests/dev/full_size_parity.py [n_sets] [n_points] [iterations]
 """
 import json
 import os
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from gadfit_b200 import LMsolver, workloads as W  # noqa: E402
 from gadfit_b200._capi import Api  # noqa: E402

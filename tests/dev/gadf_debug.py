@@ -1,7 +1,7 @@
 """Developer script (run under gpurun): gadf driver, block-arrow case, device vs oracle per trial."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import backends
 import gadfit_b200 as g

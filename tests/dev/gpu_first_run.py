@@ -2,13 +2,13 @@
 small instances and print micro-benchmarks (run under gpurun)."""
 import json, os, re, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from gadfit_b200._capi import Api, product_api
 from gadfit_b200.lm_solver import LMsolver
 from gadfit_b200 import workloads as W
 import ctypes as C
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ref = Api(os.path.join(ROOT, 'oracle/_ref/libgadfit_ref.so'), 'gadfit_ref_', product=False)
 api = product_api()
 

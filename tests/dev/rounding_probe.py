@@ -4,7 +4,7 @@ sums), and the oracle restatement with the shared block / J^T r / chi2
 accumulated in long double ("extended") -- and reports the parameter distance
 of the two double-precision solvers from the extended one.
 
-    gpurun -- python tools/rounding_probe.py [n_sets] [n_points] [iterations]
+    gpurun -- python tests/dev/rounding_probe.py [n_sets] [n_points] [iterations]
 """
 import ctypes as C
 import json
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from gadfit_b200 import LMsolver, workloads as W  # noqa: E402
 from gadfit_b200._capi import Api  # noqa: E402
