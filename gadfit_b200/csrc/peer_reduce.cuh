@@ -20,6 +20,7 @@
 // OpenCoarrays/MPI (fortran/gadfit/gadfit.F90:700-701,735,1032).
 #pragma once
 
+#include "block_arrow_kernels.cuh"
 #include "device_util.cuh"
 
 namespace gadfit_b200 {
@@ -51,16 +52,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// One CTA.  buf[0..n) is replaced by the sum over ranks.
-static __global__ void __launch_bounds__(256)
-  k_peer_all_reduce(const PeerTable t, double* __restrict__ buf, const int n, const unsigned long long seq)
+// Block-wide: buf[0..n) -- global memory this block may just have written --
+// is replaced by the sum over ranks.  Every thread of the block calls it.
+__device__ __forceinline__ void
+peer_all_reduce_block(const PeerTable& t, double* __restrict__ buf, const int n, const unsigned long long seq)
 {
     const int parity { static_cast<int>(seq & 1ULL) };
     const int tid { static_cast<int>(threadIdx.x) };
+    const int nthreads { static_cast<int>(blockDim.x) };
+    __syncthreads();
     // 1. my contribution -> every rank's mailbox (peer stores over NVLink)
     for (int q = 0; q < t.world; ++q) {
         double* dst { t.box[q]->data[parity][t.rank] };
-        for (int i = tid; i < n; i += blockDim.x) {
+        for (int i = tid; i < n; i += nthreads) {
             dst[i] = buf[i];
         }
     }
@@ -80,13 +84,61 @@ static __global__ void __launch_bounds__(256)
     // 4. sum in rank order (identical on every rank); bypass L1, the lines
     //    were written by peers
     const PeerMailbox* mine { t.box[t.rank] };
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += nthreads) {
         double sum { 0.0 };
         for (int q = 0; q < t.world; ++q) {
             sum += __ldcv(&mine->data[parity][q][i]);
         }
         buf[i] = sum;
     }
+}
+
+// One CTA.  buf[0..n) is replaced by the sum over ranks.
+static __global__ void __launch_bounds__(256)
+  k_peer_all_reduce(const PeerTable t, double* __restrict__ buf, const int n, const unsigned long long seq)
+{
+    peer_all_reduce_block(t, buf, n, seq);
+}
+
+// Reduction + collective in ONE kernel: the last stage of a deterministic
+// local reduction hands its result straight to the peers' mailboxes, so no
+// launch and no HBM round trip sits between the math and the exchange.
+//   chi2 sweep: sum of the CTA partials (k_sum_partials) + all-reduce
+static __global__ void __launch_bounds__(kThreads)
+  k_sum_partials_peer(const double* __restrict__ partials,
+                      const int n,
+                      double* __restrict__ out,
+                      const PeerTable t,
+                      const unsigned long long seq)
+{
+    __shared__ double s_red[kThreads / 32];
+    double sum { 0.0 };
+    for (int i = static_cast<int>(threadIdx.x); i < n; i += kThreads) {
+        sum += partials[i];
+    }
+    const double total { block_sum(sum, s_red) };
+    if (threadIdx.x == 0) {
+        *out = total;
+    }
+    peer_all_reduce_block(t, out, 1, seq);
+}
+//   shared block / Schur sums: last stage of k_column_sums + all-reduce
+static __global__ void __launch_bounds__(256)
+  k_column_sums_peer(const double* __restrict__ in,
+                     const int n_rows,
+                     const int V,
+                     double* __restrict__ out,
+                     const PeerTable t,
+                     const unsigned long long seq)
+{
+    for (int v = static_cast<int>(threadIdx.x); v < V; v += blockDim.x) {
+        double sum { 0.0 };
+        for (int r = 0; r < n_rows; ++r) {
+            sum += in[static_cast<long long>(r) * V + v];
+        }
+        out[v] = sum;
+    }
+    peer_all_reduce_block(t, out, V, seq);
 }
 
 // Host side: mailbox allocation and the exchange of IPC handles (through the
@@ -193,6 +245,19 @@ struct PeerReduce
     {
         ++seq;
         k_peer_all_reduce<<<1, 256, 0, stream>>>(table, buf, n, seq);
+    }
+    // fused with the last stage of the local reduction
+    auto sum_partials_all_reduce(const double* partials, const int n, double* out,
+                                 cudaStream_t stream) -> void
+    {
+        ++seq;
+        k_sum_partials_peer<<<1, kThreads, 0, stream>>>(partials, n, out, table, seq);
+    }
+    auto column_sums_all_reduce(const double* in, const int n_rows, const int V, double* out,
+                                const int threads, cudaStream_t stream) -> void
+    {
+        ++seq;
+        k_column_sums_peer<<<1, threads, 0, stream>>>(in, n_rows, V, out, table, seq);
     }
 };
 

@@ -643,6 +643,14 @@ struct SolverImpl
         if (n_tiles > 0) {
             ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr);
             launched();
+            if (world > 1 && peer.active) {
+                // final sum of the CTA partials and the all-reduce in one kernel
+                peer.sum_partials_all_reduce(d_chi2_partials.ptr, grid_chi2, dst, stream);
+                launched();
+                ++n_peer_reductions;
+                t_chi2.stop(stream);
+                return;
+            }
             k_sum_partials<<<1, kThreads, 0, stream>>>(d_chi2_partials.ptr, grid_chi2, dst);
             launched();
         } else {
@@ -652,28 +660,47 @@ struct SolverImpl
         t_chi2.stop(stream);
     }
 
-    // Deterministic column sums of contrib[n_local_sets][V] -> dst[V]
-    auto column_sums(const double* contrib, const int V, double* dst) -> void
+    // Deterministic column sums of contrib[n_local_sets][V] -> dst[V];
+    // reduce: followed by the sum over ranks -- over peer memory the last
+    // stage and the all-reduce are one kernel (peer_reduce.cuh)
+    auto column_sums(const double* contrib, const int V, double* dst, const bool reduce = false)
+      -> void
     {
         if (V == 0) {
             return;
         }
         if (n_local_sets == 0) {
             GADFIT_CUDA_TRY(cudaMemsetAsync(dst, 0, V * sizeof(double), stream));
+            if (reduce) {
+                all_reduce(dst, V);
+            }
             return;
         }
+        const bool fused { reduce && world > 1 && peer.active && V <= kPeerMaxDoubles };
         constexpr int chunk { 64 };
         const int blocks { (n_local_sets + chunk - 1) / chunk };
         const int threads { std::min(256, ((V + 31) / 32) * 32) };
-        if (blocks == 1) {
-            k_column_sums<<<1, threads, 0, stream>>>(contrib, n_local_sets, V, chunk, dst);
+        const double* last_in { contrib };
+        int last_rows { n_local_sets };
+        if (blocks > 1) {
+            d_stage.ensure(std::max(d_stage.capacity, static_cast<size_t>(blocks) * V));
+            k_column_sums<<<blocks, threads, 0, stream>>>(
+              contrib, n_local_sets, V, chunk, d_stage.ptr);
             launched();
+            last_in = d_stage.ptr;
+            last_rows = blocks;
+        }
+        if (fused) {
+            peer.column_sums_all_reduce(last_in, last_rows, V, dst, threads, stream);
+            launched();
+            ++n_peer_reductions;
             return;
         }
-        d_stage.ensure(std::max(d_stage.capacity, static_cast<size_t>(blocks) * V));
-        k_column_sums<<<blocks, threads, 0, stream>>>(contrib, n_local_sets, V, chunk, d_stage.ptr);
-        k_column_sums<<<1, threads, 0, stream>>>(d_stage.ptr, blocks, V, blocks, dst);
-        launched(2);
+        k_column_sums<<<1, threads, 0, stream>>>(last_in, last_rows, V, last_rows, dst);
+        launched();
+        if (reduce) {
+            all_reduce(dst, V);
+        }
     }
 
     [[nodiscard]] auto shared_len() const -> int { return pg * (pg + 1) / 2 + pg; }
@@ -743,10 +770,7 @@ struct SolverImpl
                                VG);
             launched();
         }
-        column_sums(d_contrib.ptr, VG, d_shared_sums.ptr);
-        if (!part.split) {
-            all_reduce(d_shared_sums.ptr, VG);
-        }
+        column_sums(d_contrib.ptr, VG, d_shared_sums.ptr, !part.split);
         t_linalg.stop(stream);
     }
 
@@ -781,10 +805,7 @@ struct SolverImpl
                                  VG);
                 launched();
             }
-            column_sums(d_contrib.ptr, VG, d_schur_sums.ptr);
-            if (!part.split) {
-                all_reduce(d_schur_sums.ptr, VG);
-            }
+            column_sums(d_contrib.ptr, VG, d_schur_sums.ptr, !part.split);
         }
         if (pg > 0) {
             k_shared_solve<<<1, 32, 0, stream>>>(pg,
@@ -857,10 +878,7 @@ struct SolverImpl
                                      2 * pg);
                 launched();
             }
-            column_sums(d_contrib.ptr, 2 * pg, d_rhs2_sums.ptr);
-            if (!part.split) {
-                all_reduce(d_rhs2_sums.ptr, 2 * pg);
-            }
+            column_sums(d_contrib.ptr, 2 * pg, d_rhs2_sums.ptr, !part.split);
             if (pg > 0) {
                 k_shared_solve<<<1, 32, 0, stream>>>(pg,
                                                      2,
@@ -893,10 +911,7 @@ struct SolverImpl
                                      d_contrib.ptr);
                 launched(2);
             }
-            column_sums(d_contrib.ptr, 2, d_ratio_sums.ptr);
-            if (!part.split) {
-                all_reduce(d_ratio_sums.ptr, 2);
-            }
+            column_sums(d_contrib.ptr, 2, d_ratio_sums.ptr, !part.split);
             k_acc_ratio_final<<<1, 32, 0, stream>>>(pg,
                                                     settings.acceleration_threshold,
                                                     d_ratio_sums.ptr,
