@@ -88,9 +88,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def wait_ready(self, timeout: float = 10.0) -> None:
+        """nvidia-smi takes 0.1-1 s to deliver its first sample (longer on an
+        8-GPU box): block until it does, so the timed region is covered."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, t_begin: float | None = None, t_end: float | None = None) -> dict:
+        """Samples taken within [t_begin, t_end] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -98,9 +106,11 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        rows = [r for t, r in self.rows
+                if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.03)]
         sm, smax, power, loaded, reasons = [], [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) < 8:
                 continue
             try:
@@ -306,6 +316,8 @@ def main_b200(args, emit):
     fp64_peak = max(dfma_peak, dmma_peak)
 
     # ---- device-resident arm: upload once, warm up, then time K iterations
+    sampler = ClockSampler(local_rank)  # started early: its first sample takes a while
+    sampler.start()
     solver = new_solver(args.warmup)
     solver.upload()
     barrier()
@@ -321,8 +333,8 @@ def main_b200(args, emit):
                 solver.setPar(k, float(w.start[s_, k]), True, s_)
 
     solver.settings.iteration_limit = args.steps
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_ready()
+    t_region_begin = time.perf_counter()
     runs = []
     for _ in range(max(args.repeats, 1)):
         reset_start()
@@ -337,7 +349,7 @@ def main_b200(args, emit):
         runs.append(dict(seconds=max_over_ranks(t_local), launches=solver.launches() - launches0,
                          k1_sec=max_over_ranks(k1_sec), k1_calls=k1_calls, tm=solver.timings(),
                          done=solver.iterations()))
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region_begin, time.perf_counter())
     comm_stats = solver.commStats() if world > 1 else None
     runs.sort(key=lambda r: r["seconds"])
     med = runs[len(runs) // 2]                      # median repeat
