@@ -199,23 +199,18 @@ __global__ void k_local_prepare(const double* __restrict__ M,
 // contribution [Y'Y (pg x pg packed upper), Y'z (pg)].  The Cholesky loop
 // order is that of the reference's in-tree dpptrf (lapack_fallback.cpp:59-81).
 template <int NP>
-__global__ void k_local_schur(const double* __restrict__ M,
-                              const unsigned* __restrict__ active,
-                              const unsigned global_mask,
-                              const int n_sets,
-                              const double* __restrict__ dtd_local,
-                              const LmState* __restrict__ state,
-                              LocalFactor<NP>* __restrict__ factors,
-                              double* __restrict__ contrib,
-                              const int VG)
+__device__ __forceinline__ void local_schur_set(const int s,
+                                                const double* __restrict__ M,
+                                                const unsigned* __restrict__ active,
+                                                const unsigned global_mask,
+                                                const double* __restrict__ dtd_local,
+                                                const double lambda,
+                                                LocalFactor<NP>* __restrict__ factors,
+                                                double* __restrict__ contrib,
+                                                const int VG)
 {
     constexpr int NA { NP + 1 };
     constexpr int NT { NA * (NA + 1) / 2 };
-    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
-    if (s >= n_sets) {
-        return;
-    }
-    const double lambda { state->lambda };
     const double* Ms { M + static_cast<long long>(s) * NT };
     int idx_g[NP];
     int idx_l[NP];
@@ -276,6 +271,24 @@ __global__ void k_local_schur(const double* __restrict__ M,
     }
 }
 
+template <int NP>
+__global__ void k_local_schur(const double* __restrict__ M,
+                              const unsigned* __restrict__ active,
+                              const unsigned global_mask,
+                              const int n_sets,
+                              const double* __restrict__ dtd_local,
+                              const LmState* __restrict__ state,
+                              LocalFactor<NP>* __restrict__ factors,
+                              double* __restrict__ contrib,
+                              const int VG)
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s < n_sets) {
+        local_schur_set<NP>(
+          s, M, active, global_mask, dtd_local, state->lambda, factors, contrib, VG);
+    }
+}
+
 // Same factor, new right-hand side J^T omega (lm_solver.cpp:383-384):
 // z'_s = R^-1 v_s[local]; contribution [v_s[global] (pg), Y' z' (pg)].
 template <int NP>
@@ -331,25 +344,24 @@ __global__ void k_local_schur_rhs(const double* __restrict__ v_sets, // [n_sets]
 // bit-identical to a one-thread implementation.
 constexpr int kMaxShared { 32 };
 
-static __global__ void __launch_bounds__(32)
-  k_shared_solve(const int pg,
-                 const int which,
-                 const int update_dtd,
-                 const int damp_max,
-                 const double* __restrict__ shared_sums,
-                 const double* __restrict__ schur_sums,
-                 const double* __restrict__ rhs2_sums,
-                 const LmState* __restrict__ state,
-                 double* __restrict__ dtd_global, // [pg]
-                 double* __restrict__ chol,       // [pg*pg]
-                 double* __restrict__ delta_g)    // [pg]
+// Called by exactly one full warp
+__device__ __forceinline__ void shared_solve_warp(const int pg,
+                                                  const int which,
+                                                  const int update_dtd,
+                                                  const int damp_max,
+                                                  const double* __restrict__ shared_sums,
+                                                  const double* __restrict__ schur_sums,
+                                                  const double* __restrict__ rhs2_sums,
+                                                  const double lambda,
+                                                  double* __restrict__ dtd_global, // [pg]
+                                                  double* __restrict__ chol,       // [pg*pg]
+                                                  double* __restrict__ delta_g,    // [pg]
+                                                  double (*s_L)[kMaxShared + 1])
 {
-    __shared__ double s_L[kMaxShared][kMaxShared + 1];
-    const int lane { static_cast<int>(threadIdx.x) };
+    const int lane { static_cast<int>(threadIdx.x) & 31 };
     const int ntri { pg * (pg + 1) / 2 };
     const bool row { lane < pg };
     if (which == 1) {
-        const double lambda { state->lambda };
         double dtd { 0.0 };
         if (row) {
             dtd = dtd_global[lane];
@@ -424,21 +436,35 @@ static __global__ void __launch_bounds__(32)
     }
 }
 
+static __global__ void __launch_bounds__(32)
+  k_shared_solve(const int pg,
+                 const int which,
+                 const int update_dtd,
+                 const int damp_max,
+                 const double* __restrict__ shared_sums,
+                 const double* __restrict__ schur_sums,
+                 const double* __restrict__ rhs2_sums,
+                 const LmState* __restrict__ state,
+                 double* __restrict__ dtd_global,
+                 double* __restrict__ chol,
+                 double* __restrict__ delta_g)
+{
+    __shared__ double s_L[kMaxShared][kMaxShared + 1];
+    shared_solve_warp(pg, which, update_dtd, damp_max, shared_sums, schur_sums, rhs2_sums,
+                      state->lambda, dtd_global, chol, delta_g, s_L);
+}
+
 // delta_s = R^-T (z - Y delta_g), scattered by model parameter index:
 // delta_par[s][k] = step of parameter k of data set s (0 if inactive);
 // global parameters get delta_g.
 template <int NP>
-__global__ void k_local_backsolve(const unsigned* __restrict__ active,
-                                  const unsigned global_mask,
-                                  const int n_sets,
-                                  const LocalFactor<NP>* __restrict__ factors,
-                                  const double* __restrict__ delta_g,
-                                  double* __restrict__ delta_par) // [n_sets][NP]
+__device__ __forceinline__ void local_backsolve_set(const int s,
+                                                    const unsigned* __restrict__ active,
+                                                    const unsigned global_mask,
+                                                    const LocalFactor<NP>* __restrict__ factors,
+                                                    const double* __restrict__ delta_g,
+                                                    double* __restrict__ delta_par) // [n_sets][NP]
 {
-    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
-    if (s >= n_sets) {
-        return;
-    }
     int idx_g[NP];
     int idx_l[NP];
     int pg;
@@ -471,6 +497,20 @@ __global__ void k_local_backsolve(const unsigned* __restrict__ active,
     }
     for (int i = 0; i < pl; ++i) {
         out[idx_l[i]] = d[i];
+    }
+}
+
+template <int NP>
+__global__ void k_local_backsolve(const unsigned* __restrict__ active,
+                                  const unsigned global_mask,
+                                  const int n_sets,
+                                  const LocalFactor<NP>* __restrict__ factors,
+                                  const double* __restrict__ delta_g,
+                                  double* __restrict__ delta_par)
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s < n_sets) {
+        local_backsolve_set<NP>(s, active, global_mask, factors, delta_g, delta_par);
     }
 }
 
