@@ -53,6 +53,20 @@ struct LocalFactor
     double z[NP];      // R^-1 b_s   (pl)
 };
 
+// Element-wise copy as a compact loop (a struct assignment unrolls into 2 x
+// (2 NP^2 + NP) instructions)
+template <int NP>
+__device__ __forceinline__ void copy_factor(LocalFactor<NP>& dst, const LocalFactor<NP>& src)
+{
+    constexpr int n { static_cast<int>(sizeof(LocalFactor<NP>) / sizeof(double)) };
+    const double* from { reinterpret_cast<const double*>(&src) };
+    double* to { reinterpret_cast<double*>(&dst) };
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        to[i] = from[i];
+    }
+}
+
 template <int NP>
 __device__ __forceinline__ void role_lists(const unsigned active,
                                            const unsigned global_mask,
@@ -107,6 +121,39 @@ static __global__ void k_reduce_slots(const double* __restrict__ partials,
     out[idx] = sum;
 }
 
+// sum_{r in [r0, r1)} in[r * stride + v] in ascending order.  The loads of 16
+// rows are issued together and then added one by one: a plain loop is a chain
+// of (L2 latency + add) per row.  Out of line on purpose: these launch-once,
+// run-once kernels are bound by cold instruction fetch (the sweeps stream
+// ~100 MB through L2 between two solves), so code size is what counts.
+static __device__ __noinline__ double ordered_column_sum(const double* in,
+                                                     const int r0,
+                                                     const int r1,
+                                                     const long long stride,
+                                                     const int v)
+{
+    constexpr int batch { 16 };
+    double sum { 0.0 };
+    int r { r0 };
+#pragma unroll 1
+    for (; r + batch <= r1; r += batch) {
+        double x[batch];
+#pragma unroll
+        for (int u = 0; u < batch; ++u) {
+            x[u] = in[static_cast<long long>(r + u) * stride + v];
+        }
+#pragma unroll
+        for (int u = 0; u < batch; ++u) {
+            sum += x[u];
+        }
+    }
+#pragma unroll 1
+    for (; r < r1; ++r) {
+        sum += in[static_cast<long long>(r) * stride + v];
+    }
+    return sum;
+}
+
 // Column sums over rows in two fixed stages: stage 1, block b sums rows
 // [b*chunk, (b+1)*chunk) for every column; stage 2 (gridDim == 1, chunk ==
 // number of stage-1 blocks) sums the block results.
@@ -119,11 +166,7 @@ static __global__ void k_column_sums(const double* __restrict__ in,
     const int r0 { static_cast<int>(blockIdx.x) * chunk };
     const int r1 { min(n_rows, r0 + chunk) };
     for (int v = static_cast<int>(threadIdx.x); v < V; v += blockDim.x) {
-        double sum { 0.0 };
-        for (int r = r0; r < r1; ++r) {
-            sum += in[static_cast<long long>(r) * V + v];
-        }
-        out[static_cast<long long>(blockIdx.x) * V + v] = sum;
+        out[static_cast<long long>(blockIdx.x) * V + v] = ordered_column_sum(in, r0, r1, V, v);
     }
 }
 
@@ -148,30 +191,27 @@ static __global__ void k_sum_partials(const double* __restrict__ partials,
 // the damping matrix and emit this data set's contribution to the shared
 // block: [G_s (pg x pg packed upper), b_g,s (pg)].
 template <int NP>
-__global__ void k_local_prepare(const double* __restrict__ M,
-                                const unsigned* __restrict__ active,
-                                const unsigned global_mask,
-                                const int n_sets,
-                                const int damp_max,
-                                double* __restrict__ dtd_local, // [n_sets][NP]
-                                double* __restrict__ contrib,   // [n_sets][VG]
-                                const int VG)
+__device__ __forceinline__ void local_prepare_set(const int s,
+                                                  const int lane,
+                                                  const int stride,
+                                                  const double* __restrict__ M,
+                                                  const unsigned* __restrict__ active,
+                                                  const unsigned global_mask,
+                                                  const int damp_max,
+                                                  double* __restrict__ dtd_local, // [n_sets][NP]
+                                                  double* __restrict__ contrib,   // [n_sets][VG]
+                                                  const int VG)
 {
-    // One WARP per data set, lanes over the output entries (pure gather)
+    // `stride` lanes per data set over the output entries (pure gather)
     constexpr int NA { NP + 1 };
     constexpr int NT { NA * (NA + 1) / 2 };
-    const int s { static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5) };
-    const int lane { static_cast<int>(threadIdx.x) & 31 };
-    if (s >= n_sets) {
-        return;
-    }
     const double* Ms { M + static_cast<long long>(s) * NT };
     int idx_g[NP];
     int idx_l[NP];
     int pg;
     int pl;
     role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
-    for (int a = lane; a < pl; a += 32) {
+    for (int a = lane; a < pl; a += stride) {
         const int k { idx_l[a] };
         const double jtj { Ms[tri_index(NA, k, k)] };
         double* d { dtd_local + static_cast<long long>(s) * NP + k };
@@ -180,7 +220,7 @@ __global__ void k_local_prepare(const double* __restrict__ M,
     }
     double* out { contrib + static_cast<long long>(s) * VG };
     const int ntri { pg * (pg + 1) / 2 };
-    for (int o = lane; o < VG; o += 32) {
+    for (int o = lane; o < VG; o += stride) {
         if (o < ntri) {
             int a { 0 };
             int rem { o };
@@ -195,33 +235,62 @@ __global__ void k_local_prepare(const double* __restrict__ M,
     }
 }
 
+template <int NP>
+__global__ void k_local_prepare(const double* __restrict__ M,
+                                const unsigned* __restrict__ active,
+                                const unsigned global_mask,
+                                const int n_sets,
+                                const int damp_max,
+                                double* __restrict__ dtd_local,
+                                double* __restrict__ contrib,
+                                const int VG)
+{
+    const int s { static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5) };
+    if (s < n_sets) {
+        local_prepare_set<NP>(s, static_cast<int>(threadIdx.x) & 31, 32, M, active, global_mask,
+                              damp_max, dtd_local, contrib, VG);
+    }
+}
+
 // Per trial step: factorise the damped local block and emit the Schur
 // contribution [Y'Y (pg x pg packed upper), Y'z (pg)].  The Cholesky loop
 // order is that of the reference's in-tree dpptrf (lapack_fallback.cpp:59-81).
 template <int NP>
-__device__ __forceinline__ void local_schur_set(const int s,
-                                                const double* __restrict__ M,
-                                                const unsigned* __restrict__ active,
-                                                const unsigned global_mask,
-                                                const double* __restrict__ dtd_local,
-                                                const double lambda,
-                                                LocalFactor<NP>* __restrict__ factors,
-                                                double* __restrict__ contrib,
-                                                const int VG)
+__device__ __forceinline__ void local_schur_into(LocalFactor<NP>& F,
+                                                 const int s,
+                                                 const double* __restrict__ M,
+                                                 const unsigned* __restrict__ active,
+                                                 const unsigned global_mask,
+                                                 const double* __restrict__ dtd_local,
+                                                 const double lambda,
+                                                 double* __restrict__ contrib,
+                                                 const int VG)
 {
     constexpr int NA { NP + 1 };
     constexpr int NT { NA * (NA + 1) / 2 };
     const double* Ms { M + static_cast<long long>(s) * NT };
+    // (small NP: all of M_s in one burst of loads instead of on demand inside
+    // the dependent chains below)
+    double m_local[NP <= 8 ? NT : 1];
+    if constexpr (NP <= 8) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            m_local[t] = Ms[t];
+        }
+        Ms = m_local;
+    }
     int idx_g[NP];
     int idx_l[NP];
     int pg;
     int pl;
     role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
-    LocalFactor<NP>& F { factors[s] };
     // R R' = L_s + lambda D_s
+#pragma unroll 1
     for (int i = 0; i < pl; ++i) {
+#pragma unroll 1
         for (int j = 0; j < i; ++j) {
             double v { m_entry(Ms, NA, idx_l[i], idx_l[j]) };
+#pragma unroll 1
             for (int k = 0; k < j; ++k) {
                 v -= F.R[i * NP + k] * F.R[j * NP + k];
             }
@@ -229,6 +298,7 @@ __device__ __forceinline__ void local_schur_set(const int s,
         }
         double v { Ms[tri_index(NA, idx_l[i], idx_l[i])]
                    + lambda * dtd_local[static_cast<long long>(s) * NP + idx_l[i]] };
+#pragma unroll 1
         for (int k = 0; k < i; ++k) {
             v -= F.R[i * NP + k] * F.R[i * NP + k];
         }
@@ -236,10 +306,13 @@ __device__ __forceinline__ void local_schur_set(const int s,
     }
     // Y = R^-1 C_s' and z = R^-1 b_s (forward substitution,
     // lapack_fallback.cpp:88-95)
+#pragma unroll 1
     for (int g = 0; g <= pg; ++g) {
         const int col { g < pg ? idx_g[g] : NP };
+#pragma unroll 1
         for (int i = 0; i < pl; ++i) {
             double v { m_entry(Ms, NA, idx_l[i], col) };
+#pragma unroll 1
             for (int j = 0; j < i; ++j) {
                 v -= F.R[i * NP + j] * (g < pg ? F.Y[j * NP + g] : F.z[j]);
             }
@@ -253,21 +326,50 @@ __device__ __forceinline__ void local_schur_set(const int s,
     }
     double* out { contrib + static_cast<long long>(s) * VG };
     int o { 0 };
+#pragma unroll 1
     for (int a = 0; a < pg; ++a) {
+#pragma unroll 1
         for (int b = a; b < pg; ++b) {
             double v { 0.0 };
+#pragma unroll 1
             for (int i = 0; i < pl; ++i) {
                 v += F.Y[i * NP + a] * F.Y[i * NP + b];
             }
             out[o++] = v;
         }
     }
+#pragma unroll 1
     for (int a = 0; a < pg; ++a) {
         double v { 0.0 };
+#pragma unroll 1
         for (int i = 0; i < pl; ++i) {
             v += F.Y[i * NP + a] * F.z[i];
         }
         out[o++] = v;
+    }
+}
+
+// The factorisation is a chain of dependent read-modify-writes of R, Y, z.
+// Up to 8 parameters it runs in thread-local storage (L1-resident) and is
+// stored once; in global memory every link of the chain is an L2 round trip.
+template <int NP>
+__device__ __forceinline__ void local_schur_set(const int s,
+                                                const double* __restrict__ M,
+                                                const unsigned* __restrict__ active,
+                                                const unsigned global_mask,
+                                                const double* __restrict__ dtd_local,
+                                                const double lambda,
+                                                LocalFactor<NP>* __restrict__ factors,
+                                                double* __restrict__ contrib,
+                                                const int VG)
+{
+    if constexpr (NP <= 8) {
+        LocalFactor<NP> F;
+        local_schur_into<NP>(F, s, M, active, global_mask, dtd_local, lambda, contrib, VG);
+        copy_factor<NP>(factors[s], F);
+    } else {
+        local_schur_into<NP>(
+          factors[s], s, M, active, global_mask, dtd_local, lambda, contrib, VG);
     }
 }
 
@@ -311,19 +413,24 @@ __global__ void k_local_schur_rhs(const double* __restrict__ v_sets, // [n_sets]
     role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
     LocalFactor<NP>& F { factors[s] };
     const double* vs { v_sets + static_cast<long long>(s) * NP };
+#pragma unroll 1
     for (int i = 0; i < pl; ++i) {
         double v { vs[idx_l[i]] };
+#pragma unroll 1
         for (int j = 0; j < i; ++j) {
             v -= F.R[i * NP + j] * F.z[j];
         }
         F.z[i] = v / F.R[i * NP + i];
     }
     double* out { contrib + static_cast<long long>(s) * VG2 };
+#pragma unroll 1
     for (int a = 0; a < pg; ++a) {
         out[a] = vs[idx_g[a]];
     }
+#pragma unroll 1
     for (int a = 0; a < pg; ++a) {
         double v { 0.0 };
+#pragma unroll 1
         for (int i = 0; i < pl; ++i) {
             v += F.Y[i * NP + a] * F.z[i];
         }
@@ -371,6 +478,7 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
                 dtd_global[lane] = dtd;
             }
             // Row `lane` of the lower triangle of the damped, Schur-reduced matrix
+#pragma unroll 1
             for (int j = 0; j <= lane; ++j) {
                 const int o { tri_index(pg, j, lane) };
                 double v { shared_sums[o] - schur_sums[o] };
@@ -381,10 +489,12 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
             }
         }
         __syncwarp();
+#pragma unroll 1
         for (int j = 0; j < pg; ++j) {
             double v { 0.0 };
             if (row && lane >= j) {
                 v = s_L[lane][j];
+#pragma unroll 1
                 for (int k = 0; k < j; ++k) {
                     v -= s_L[lane][k] * s_L[j][k];
                 }
@@ -396,12 +506,14 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
             __syncwarp();
         }
         if (row) {
+#pragma unroll 1
             for (int j = 0; j <= lane; ++j) {
                 chol[lane * pg + j] = s_L[lane][j];
             }
         }
     } else {
         if (row) {
+#pragma unroll 1
             for (int j = 0; j <= lane; ++j) {
                 s_L[lane][j] = chol[lane * pg + j];
             }
@@ -414,6 +526,7 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
         v = which == 1 ? shared_sums[ntri + lane] - schur_sums[ntri + lane]
                        : rhs2_sums[lane] - rhs2_sums[pg + lane];
     }
+#pragma unroll 1
     for (int j = 0; j < pg; ++j) {
         const double yj { __shfl_sync(0xffffffffU, v, j) / s_L[j][j] };
         if (lane == j) {
@@ -423,6 +536,7 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
         }
     }
     // Backward substitution L' x = y
+#pragma unroll 1
     for (int i = pg - 1; i >= 0; --i) {
         const double xi { __shfl_sync(0xffffffffU, v, i) / s_L[i][i] };
         if (lane == i) {
@@ -458,30 +572,33 @@ static __global__ void __launch_bounds__(32)
 // delta_par[s][k] = step of parameter k of data set s (0 if inactive);
 // global parameters get delta_g.
 template <int NP>
-__device__ __forceinline__ void local_backsolve_set(const int s,
-                                                    const unsigned* __restrict__ active,
-                                                    const unsigned global_mask,
-                                                    const LocalFactor<NP>* __restrict__ factors,
-                                                    const double* __restrict__ delta_g,
-                                                    double* __restrict__ delta_par) // [n_sets][NP]
+__device__ __forceinline__ void local_backsolve_with(const LocalFactor<NP>& F,
+                                                     const int s,
+                                                     const unsigned* __restrict__ active,
+                                                     const unsigned global_mask,
+                                                     const double* __restrict__ delta_g,
+                                                     double* __restrict__ delta_par) // [n_sets][NP]
 {
     int idx_g[NP];
     int idx_l[NP];
     int pg;
     int pl;
     role_lists<NP>(active[s], global_mask, idx_g, pg, idx_l, pl);
-    const LocalFactor<NP>& F { factors[s] };
     double d[NP];
+#pragma unroll 1
     for (int i = 0; i < pl; ++i) {
         double v { F.z[i] };
+#pragma unroll 1
         for (int a = 0; a < pg; ++a) {
             v -= F.Y[i * NP + a] * delta_g[a];
         }
         d[i] = v;
     }
     // Backward substitution, lapack_fallback.cpp:96-104
+#pragma unroll 1
     for (int i = pl - 1; i >= 0; --i) {
         double v { d[i] };
+#pragma unroll 1
         for (int j = pl - 1; j > i; --j) {
             v -= F.R[j * NP + i] * d[j];
         }
@@ -497,6 +614,23 @@ __device__ __forceinline__ void local_backsolve_set(const int s,
     }
     for (int i = 0; i < pl; ++i) {
         out[idx_l[i]] = d[i];
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ void local_backsolve_set(const int s,
+                                                    const unsigned* __restrict__ active,
+                                                    const unsigned global_mask,
+                                                    const LocalFactor<NP>* __restrict__ factors,
+                                                    const double* __restrict__ delta_g,
+                                                    double* __restrict__ delta_par)
+{
+    if constexpr (NP <= 8) {
+        LocalFactor<NP> F;
+        copy_factor<NP>(F, factors[s]); // independent loads, in flight together
+        local_backsolve_with<NP>(F, s, active, global_mask, delta_g, delta_par);
+    } else {
+        local_backsolve_with<NP>(factors[s], s, active, global_mask, delta_g, delta_par);
     }
 }
 
@@ -641,6 +775,292 @@ static __global__ void k_revert_if_rejected(const long long n,
     const long long i { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
     if (i < n) {
         par[i] = par_old[i];
+    }
+}
+
+// ---- fused kernels of the latency-bound regime ------------------------------
+//
+// With a few thousand data sets on one GPU (BASELINE config 3: 1000 x 4096)
+// the sweeps take tens of microseconds and a trial step was a chain of
+// sixteen few-microsecond launches.  Everything between the Jacobian sweep and
+// the chi2 sweep of a trial is ONE launch here (k_solve_small), everything
+// after the chi2 sweep another (k_finish_trial): four launches per iteration.
+//
+// k_solve_small is one thread-block cluster of 8 CTAs: the per-data-set work
+// (one thread per data set, strided 200-byte records) is spread over eight
+// SMs' load/store units, the stages are separated by the hardware cluster
+// barrier (release/acquire at cluster scope, so global-memory results of one
+// stage are visible to the next) instead of kernel boundaries.  A single CTA
+// was tried first: 179 us per solve on config 3 against 62 us for the launch
+// chain -- one SM cannot keep that many scattered loads in flight.
+//
+// Each stage is the per-data-set body of the kernel it replaces and the sums
+// run in the same order (slots; 64-row chunks, then chunk results), so the
+// results are bit-identical to the multi-kernel path.
+constexpr int kSmallThreads { 512 };    // per CTA: slot reduction, column sums
+constexpr int kSmallSetThreads { 128 }; // of which own one data set each per pass
+constexpr int kSmallCtas { 8 };
+constexpr int kSmallMaxSets { 4096 };
+constexpr int kColumnChunk { 64 };
+static_assert(kSmallSetThreads % kColumnChunk == 0, "a CTA owns whole chunks");
+
+struct SmallSolveArgs
+{
+    int n_sets;
+    int pg;
+    int VG;             // pg (pg + 1) / 2 + pg
+    unsigned global_mask;
+    int prepare;        // first trial of an iteration: slots -> M, damping, shared sums
+    int has_locals;     // some data set has local parameters (Schur step needed)
+    int update;         // apply delta1 to the parameters (no acceleration)
+    int damp_max;
+    const double* jac_partials;
+    const int* slot_first;
+    const int* slot_count;
+    const unsigned* active;
+    double* M;
+    double* dtd_local;
+    double* contrib;    // [2][n_sets][VG]: shared-block rows, Schur rows
+    double* stage;      // [2][ceil(n_sets / 64)][VG]
+    double* shared_sums;
+    double* schur_sums;
+    LmState* state;
+    double* dtd_global;
+    double* chol;
+    double* delta_g;
+    void* factors;
+    double* delta_par;
+    double* par;
+    double* par_old;
+    double* par_jac;
+};
+
+// Stage 1 of k_column_sums for the chunks whose rows this CTA produced
+// (data set s belongs to CTA (s / 128) % 8, so chunk b to CTA (b % 16) / 2)
+__device__ __forceinline__ void column_sums_own_chunks(const int cta,
+                                                       const double* in,
+                                                       const int n_rows,
+                                                       const int V,
+                                                       double* stage)
+{
+    constexpr int per_cta { kSmallSetThreads / kColumnChunk };
+    const int blocks { (n_rows + kColumnChunk - 1) / kColumnChunk };
+    if (blocks <= 1) {
+        return;
+    }
+#pragma unroll 1
+    for (int b0 = per_cta * cta; b0 < blocks; b0 += per_cta * kSmallCtas) {
+#pragma unroll 1
+        for (int item = static_cast<int>(threadIdx.x); item < per_cta * V; item += kSmallThreads) {
+            const int j { item / V };
+            const int v { item - j * V };
+            const int b { b0 + j };
+            if (b < blocks) {
+                const int r1 { min(n_rows, (b + 1) * kColumnChunk) };
+                stage[static_cast<long long>(b) * V + v] =
+                  ordered_column_sum(in, b * kColumnChunk, r1, V, v);
+            }
+        }
+    }
+}
+
+// Stage 2 of k_column_sums by one CTA
+__device__ __forceinline__ void column_sums_final(const double* in,
+                                                  const double* stage,
+                                                  const int n_rows,
+                                                  const int V,
+                                                  double* out)
+{
+    const int blocks { (n_rows + kColumnChunk - 1) / kColumnChunk };
+    const double* last_in { blocks > 1 ? stage : in };
+    const int last_rows { blocks > 1 ? blocks : n_rows };
+#pragma unroll 1
+    for (int v = static_cast<int>(threadIdx.x); v < V; v += kSmallThreads) {
+        out[v] = ordered_column_sum(last_in, 0, last_rows, V, v);
+    }
+}
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    // release / acquire at cluster scope (the PTX defaults, spelled out)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;\n" ::
+                   : "memory");
+}
+
+// k_reduce_slots + k_local_prepare + column sums (first trial), k_local_schur
+// + column sums, k_shared_solve, k_local_backsolve, k_update_parameters
+template <int NP>
+__global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThreads)
+  k_solve_small(const SmallSolveArgs a)
+{
+    constexpr int NA { NP + 1 };
+    constexpr int NT { NA * (NA + 1) / 2 };
+    constexpr int cluster_threads { kSmallCtas * kSmallThreads };
+    constexpr int sets_per_pass { kSmallCtas * kSmallSetThreads };
+    __shared__ double s_L[kMaxShared][kMaxShared + 1];
+    const int tid { static_cast<int>(threadIdx.x) };
+    const int cta { static_cast<int>(blockIdx.x) }; // grid == one cluster
+    const int g { cta * kSmallThreads + tid };
+    const int n_par { a.n_sets * NP };
+    const int chunks { (a.n_sets + kColumnChunk - 1) / kColumnChunk };
+    // the data set this thread owns in the first pass (threads >= 128: none)
+    const int my_set { tid < kSmallSetThreads ? cta * kSmallSetThreads + tid : a.n_sets };
+    LocalFactor<NP>* factors { static_cast<LocalFactor<NP>*>(a.factors) };
+    double* contrib_schur { a.contrib + static_cast<long long>(a.n_sets) * a.VG };
+    double* stage_schur { a.stage + static_cast<long long>(chunks) * a.VG };
+    if (a.prepare != 0) {
+#pragma unroll 2
+        for (int i = g; i < n_par; i += cluster_threads) {
+            a.par_jac[i] = a.par[i];
+        }
+        // k_reduce_slots, four entries per thread at a time so that their
+        // (dependent) index and partial loads overlap; each entry still adds
+        // its slots in ascending order
+        const int n_items { a.n_sets * NT };
+#pragma unroll 1
+        for (int base = g; base < n_items; base += 4 * cluster_threads) {
+            int first[4];
+            int count[4];
+            int col[4];
+            double sum[4];
+            int max_count { 0 };
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx { base + u * cluster_threads };
+                const bool valid { idx < n_items };
+                const int s { valid ? idx / NT : 0 };
+                col[u] = idx - s * NT;
+                first[u] = a.slot_first[s];
+                count[u] = valid ? a.slot_count[s] : 0;
+                max_count = max(max_count, count[u]);
+                sum[u] = 0.0;
+            }
+#pragma unroll 1
+            for (int c = 0; c < max_count; ++c) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (c < count[u]) {
+                        sum[u] += a.jac_partials[static_cast<long long>(first[u] + c) * NT + col[u]];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx { base + u * cluster_threads };
+                if (idx < n_items) {
+                    a.M[idx] = sum[u];
+                }
+            }
+        }
+        cluster_barrier();
+        // k_local_prepare.  More than one chunk: 4 lanes per data set, inside
+        // the CTA that owns it (which then sums the rows of its chunks);
+        // a single chunk (all of it owned by CTA 0, no stage 1): 8 lanes per data set
+        if (chunks > 1) {
+            constexpr int lanes { kSmallThreads / kSmallSetThreads };
+            for (int s = cta * kSmallSetThreads + tid / lanes; s < a.n_sets; s += sets_per_pass) {
+                local_prepare_set<NP>(s, tid % lanes, lanes, a.M, a.active, a.global_mask,
+                                      a.damp_max, a.dtd_local, a.contrib, a.VG);
+            }
+        } else if (cta == 0) {
+            constexpr int lanes { kSmallThreads / kColumnChunk };
+            if (tid / lanes < a.n_sets) {
+                local_prepare_set<NP>(tid / lanes, tid % lanes, lanes, a.M, a.active,
+                                      a.global_mask, a.damp_max, a.dtd_local, a.contrib, a.VG);
+            }
+        }
+        __syncthreads();
+        column_sums_own_chunks(cta, a.contrib, a.n_sets, a.VG, a.stage);
+    }
+    const double lambda { a.state->lambda };
+    if (a.has_locals != 0) {
+        for (int s = my_set; s < a.n_sets; s += sets_per_pass) {
+            local_schur_set<NP>(
+              s, a.M, a.active, a.global_mask, a.dtd_local, lambda, factors, contrib_schur, a.VG);
+        }
+        __syncthreads();
+        column_sums_own_chunks(cta, contrib_schur, a.n_sets, a.VG, stage_schur);
+    }
+    cluster_barrier();
+    if (cta == 0) {
+        if (a.prepare != 0) {
+            column_sums_final(a.contrib, a.stage, a.n_sets, a.VG, a.shared_sums);
+        }
+        if (a.has_locals != 0) {
+            column_sums_final(contrib_schur, stage_schur, a.n_sets, a.VG, a.schur_sums);
+        }
+        __syncthreads();
+        if (tid < 32 && a.pg > 0) {
+            shared_solve_warp(a.pg, 1, a.prepare, a.damp_max, a.shared_sums, a.schur_sums, nullptr,
+                              lambda, a.dtd_global, a.chol, a.delta_g, s_L);
+        }
+    }
+    cluster_barrier();
+    for (int s = my_set; s < a.n_sets; s += sets_per_pass) {
+        local_backsolve_set<NP>(s, a.active, a.global_mask, factors, a.delta_g, a.delta_par);
+        if (a.update != 0) {
+            // saveParameters (first trial) + updateParameters,
+            // lm_solver.cpp:192-204,230-253
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const int i { s * NP + k };
+                const double p { a.par[i] };
+                if (a.prepare != 0) {
+                    a.par_old[i] = p;
+                }
+                a.par[i] = p + a.delta_par[i];
+            }
+        }
+    }
+}
+
+// k_sum_partials + k_decide + k_revert_if_rejected
+static __global__ void __launch_bounds__(kThreads)
+  k_finish_trial(const double* partials,
+                 const int n_partials,
+                 const int lambda_incs,
+                 const double lambda_down,
+                 const double lambda_up,
+                 LmState* state,
+                 const long long n_par,
+                 const double* par_old,
+                 double* par)
+{
+    __shared__ double s_red[kThreads / 32];
+    __shared__ int s_decision;
+    double sum { 0.0 };
+    for (int i = static_cast<int>(threadIdx.x); i < n_partials; i += kThreads) {
+        sum += partials[i];
+    }
+    const double total { block_sum(sum, s_red) };
+    if (threadIdx.x == 0) {
+        LmState s { *state };
+        s.new_chi2 = total;
+        LmState rec { s };
+        if (s.new_chi2 < s.old_chi2) {
+            s.lambda /= lambda_down;
+            s.old_chi2 = s.new_chi2;
+            s.decision = 0;
+            s.i_lambda = 0;
+        } else if (s.i_lambda < lambda_incs) {
+            s.lambda *= lambda_up;
+            s.decision = 1;
+            s.i_lambda += 1;
+        } else {
+            s.decision = 2;
+            s.i_lambda = 0;
+        }
+        rec.decision = s.decision;
+        state[0] = s;
+        state[1] = rec;
+        s_decision = s.decision;
+    }
+    __syncthreads();
+    if (s_decision != 0) {
+        for (long long i = threadIdx.x; i < n_par; i += kThreads) {
+            par[i] = par_old[i];
+        }
     }
 }
 

@@ -87,6 +87,9 @@ struct ModelOps
                                  const double* delta1_par,
                                  const double* delta2_par,
                                  double* contrib) const -> void = 0;
+    // Latency-bound regime: everything between the Jacobian sweep and the chi2
+    // sweep of a trial step in one launch of one cluster (block_arrow_kernels.cuh)
+    virtual auto solve_small(cudaStream_t st, const SmallSolveArgs& a) const -> void = 0;
 };
 
 inline auto blocks_for(const long long n, const int threads) -> int
@@ -280,6 +283,10 @@ struct ModelOpsImpl final : ModelOps
     {
         k_acc_ratio_local<NP><<<blocks_for(n_sets, kSetThreads), kSetThreads, 0, st>>>(
           active, global_mask, n_sets, dtd_local, delta1_par, delta2_par, contrib);
+    }
+    auto solve_small(cudaStream_t st, const SmallSolveArgs& a) const -> void override
+    {
+        k_solve_small<NP><<<kSmallCtas, kSmallThreads, 0, st>>>(a); // one cluster
     }
 };
 

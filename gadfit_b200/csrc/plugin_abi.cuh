@@ -4,8 +4,8 @@
 
 #include "model_ops.cuh"
 
-// Bumped whenever ModelOps, SweepArgs, LmState or LocalFactor change
-#define GADFIT_B200_PLUGIN_ABI_VERSION 1
+// Bumped whenever ModelOps, SweepArgs, SmallSolveArgs, LmState or LocalFactor change
+#define GADFIT_B200_PLUGIN_ABI_VERSION 2
 
 namespace gadfit_b200::plugin {
 

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <charconv>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iomanip>
 #include <limits>
@@ -940,6 +941,105 @@ struct SolverImpl
         }
     }
 
+    // ---- latency-bound regime (block_arrow_kernels.cuh, "fused kernels") ----
+
+    // One GPU, at most kSmallMaxSets data sets, no acceleration: a trial step
+    // is Jacobian sweep | k_solve_small | chi2 sweep | k_finish_trial.
+    // GADFIT_B200_FUSED=0 keeps the one-kernel-per-stage path (A/B runs, and the
+    // parity test that both paths give bit-identical results).
+    [[nodiscard]] auto small_path() const -> bool
+    {
+        const char* e { std::getenv("GADFIT_B200_FUSED") }; // read at every fit()
+        const bool allowed { e == nullptr || std::strcmp(e, "0") != 0 };
+        return allowed && world == 1 && !part.split && n_tiles > 0 && n_local_sets > 0
+               && n_local_sets <= kSmallMaxSets && settings.acceleration_threshold <= 0.0;
+    }
+
+    // The Jacobian sweep alone; its partial slots are reduced by k_solve_small
+    auto jacobian_sweep_small() -> void
+    {
+        t_jacobian.start(stream);
+        ops->jacobian(slots_jac.grid,
+                      stream,
+                      sweep_args(),
+                      settings.loss,
+                      slots_jac.base.ptr,
+                      d_jac_partials.ptr,
+                      nullptr,
+                      nullptr,
+                      n_local_points);
+        t_jacobian.stop(stream);
+        launched();
+    }
+
+    auto solve_small(const bool first_trial) -> void
+    {
+        const int VG { shared_len() };
+        const int chunks { (n_local_sets + kColumnChunk - 1) / kColumnChunk };
+        t_linalg.start(stream);
+        if (first_trial) {
+            d_contrib.ensure(2 * static_cast<size_t>(n_local_sets) * std::max(VG, 2));
+            d_stage.ensure(
+              std::max(d_stage.capacity, 2 * static_cast<size_t>(chunks) * std::max(VG, 1)));
+            d_shared_sums.ensure(std::max(VG, 1));
+            if (n_active > pg) {
+                d_schur_sums.ensure(std::max(VG, 1));
+            } else {
+                d_schur_sums.zero(std::max(VG, 1), stream);
+            }
+        }
+        SmallSolveArgs a {};
+        a.n_sets = n_local_sets;
+        a.pg = pg;
+        a.VG = VG;
+        a.global_mask = global_mask;
+        a.prepare = first_trial ? 1 : 0;
+        a.has_locals = n_active > pg ? 1 : 0;
+        a.update = 1;
+        a.damp_max = settings.damp_max;
+        a.jac_partials = d_jac_partials.ptr;
+        a.slot_first = slots_jac.first.ptr;
+        a.slot_count = slots_jac.count.ptr;
+        a.active = d_active.ptr;
+        a.M = d_M.ptr;
+        a.dtd_local = d_dtd_local.ptr;
+        a.contrib = d_contrib.ptr;
+        a.stage = d_stage.ptr;
+        a.shared_sums = d_shared_sums.ptr;
+        a.schur_sums = d_schur_sums.ptr;
+        a.state = d_state.ptr;
+        a.dtd_global = d_dtd_global.ptr;
+        a.chol = d_chol.ptr;
+        a.delta_g = d_delta1_g.ptr;
+        a.factors = d_factors.ptr;
+        a.delta_par = d_delta1_par.ptr;
+        a.par = d_par.ptr;
+        a.par_old = d_par_old.ptr;
+        a.par_jac = d_par_jac.ptr;
+        ops->solve_small(stream, a);
+        launched();
+        t_linalg.stop(stream);
+    }
+
+    // chi2 sweep of the trial step, then the last stage of its sum, the
+    // accept / reject decision and the revert in one launch
+    auto chi2_decide_small() -> void
+    {
+        t_chi2.start(stream);
+        ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr);
+        k_finish_trial<<<1, kThreads, 0, stream>>>(d_chi2_partials.ptr,
+                                                   grid_chi2,
+                                                   settings.lambda_incs,
+                                                   settings.lambda_down,
+                                                   settings.lambda_up,
+                                                   d_state.ptr,
+                                                   static_cast<long long>(n_local_sets) * NP,
+                                                   d_par_old.ptr,
+                                                   d_par.ptr);
+        launched(2);
+        t_chi2.stop(stream);
+    }
+
     // The initial values of the damping matrix (lm_solver.cpp:414,424-428)
     auto init_damping() -> void
     {
@@ -1157,6 +1257,7 @@ struct SolverImpl
         double lambda { lambda0 };
         double last_old_chi2 { 0.0 };
 
+        const bool small { small_path() };
         t_main.start(stream);
         chi2_phase(&d_state.ptr->new_chi2);
         k_copy_chi2_to_old<<<1, 1, 0, stream>>>(d_state.ptr);
@@ -1165,23 +1266,31 @@ struct SolverImpl
         bool finished { settings.iteration_limit == 0 };
         while (!finished) {
             ++i_iteration;
-            jacobian_phase(accelerate, false);
+            if (small) {
+                jacobian_sweep_small();
+            } else {
+                jacobian_phase(accelerate, false);
+            }
             lambda_lhs = lambda;
-            solve_phase(true);
+            small ? solve_small(true) : solve_phase(true);
             for (int i_lambda = 0; i_lambda <= settings.lambda_incs; ++i_lambda) {
-                chi2_phase(&d_state.ptr->new_chi2);
-                k_decide<<<1, 1, 0, stream>>>(settings.lambda_incs,
-                                              settings.lambda_down,
-                                              settings.lambda_up,
-                                              d_state.ptr,
-                                              d_state.ptr + 1);
-                const long long n { static_cast<long long>(n_local_sets) * NP };
-                if (n > 0) {
-                    k_revert_if_rejected<<<blocks_for(n, 256), 256, 0, stream>>>(
-                      n, d_state.ptr, d_par_old.ptr, d_par.ptr);
+                if (small) {
+                    chi2_decide_small();
+                } else {
+                    chi2_phase(&d_state.ptr->new_chi2);
+                    k_decide<<<1, 1, 0, stream>>>(settings.lambda_incs,
+                                                  settings.lambda_down,
+                                                  settings.lambda_up,
+                                                  d_state.ptr,
+                                                  d_state.ptr + 1);
+                    const long long n { static_cast<long long>(n_local_sets) * NP };
+                    if (n > 0) {
+                        k_revert_if_rejected<<<blocks_for(n, 256), 256, 0, stream>>>(
+                          n, d_state.ptr, d_par_old.ptr, d_par.ptr);
+                        launched();
+                    }
                     launched();
                 }
-                launched();
                 // One small record per trial step: [1] = state before the
                 // decision (+ the decision), [0] = state after it
                 GADFIT_CUDA_TRY(cudaMemcpyAsync(h_mirror,
@@ -1205,7 +1314,7 @@ struct SolverImpl
                 }
                 if (rec.decision == 1) {
                     lambda_lhs = lambda;
-                    solve_phase(false);
+                    small ? solve_small(false) : solve_phase(false);
                 } else {
                     if (chatty) { // lm_solver.cpp:484-488
                         log_line("Lambda increased " + std::to_string(settings.lambda_incs)
@@ -2152,7 +2261,9 @@ int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
                                      int* launches)
 {
     return guarded(solver, [&] {
-        const auto& t { solver->t_jac_kernel };
+        // (fused small-problem path: the Jacobian phase is exactly the kernel)
+        const auto& t { solver->t_jac_kernel.calls > 0 ? solver->t_jac_kernel
+                                                        : solver->t_jacobian };
         *launches = t.calls;
         *seconds_per_launch = t.calls > 0 ? t.seconds / t.calls : 0.0;
     });

@@ -257,3 +257,37 @@ def test_step_vectors_and_omega_with_acceleration(c1):
     np.testing.assert_allclose(a.getDelta1(), b.getDelta1(), rtol=1e-9, atol=1e-14)
     np.testing.assert_allclose(a.getDelta2(), b.getDelta2(), rtol=1e-8, atol=1e-14)
     np.testing.assert_allclose(a.getOmega(), b._array(9), rtol=1e-9, atol=1e-16)
+
+
+def _is_accelerated(sc):
+    """Geodesic acceleration (an omega sweep in the middle of the solve) keeps
+    the stage-wise path."""
+    return (sc.get("workload") == "C4"
+            or (sc.get("settings") or {}).get("acceleration_threshold", -1.0) > 0.0)
+
+
+@pytest.mark.parametrize(
+    "sc",
+    [s for s in scenarios.ALL_SCENARIOS if not _is_accelerated(s)]
+    + [dict(name="C3_small", kind="workload", workload="C3", kwargs=dict(n_sets=300, n_points=700)),
+       dict(name="C5_small", kind="workload", workload="C5", kwargs=dict(n_sets=250, n_points=96)),
+       dict(name="C2_small", kind="workload", workload="C2", kwargs=dict(n_sets=5, n_points=20_000))],
+    ids=lambda s: s["name"])
+def test_fused_small_problem_path_is_bit_identical_to_the_stagewise_path(sc, c1, monkeypatch):
+    """The latency-bound regime (one GPU, <= 4096 data sets, no acceleration)
+    runs a trial step as 4 launches (k_solve_small / k_finish_trial) instead of
+    16.  Same per-data-set code, same summation order: every trial record and
+    every parameter must be identical to the last bit, with fewer launches."""
+    monkeypatch.setenv("GADFIT_B200_FUSED", "1")
+    fused, fs = scenarios.run(sc, backends.product_solver(), c1)
+    monkeypatch.setenv("GADFIT_B200_FUSED", "0")
+    staged, ss = scenarios.run(sc, backends.product_solver(), c1)
+    assert fused["trace"] == staged["trace"]
+    assert fused["chi2"] == staged["chi2"]
+    assert fused["pars"] == staged["pars"]
+    assert fused["iterations"] == staged["iterations"]
+    assert 0 < fs.launches() <= ss.launches()
+    assert fused["iterations"] == 0 or fs.launches() < ss.launches()
+    for getter in ("getJTJ", "getDTD", "getRightSide", "getLeftSide"):
+        if fused["dof"] < 10_000:  # dense getters: small cases only
+            np.testing.assert_array_equal(getattr(fs, getter)(), getattr(ss, getter)())
