@@ -53,20 +53,6 @@ struct LocalFactor
     double z[NP];      // R^-1 b_s   (pl)
 };
 
-// Element-wise copy as a compact loop (a struct assignment unrolls into 2 x
-// (2 NP^2 + NP) instructions)
-template <int NP>
-__device__ __forceinline__ void copy_factor(LocalFactor<NP>& dst, const LocalFactor<NP>& src)
-{
-    constexpr int n { static_cast<int>(sizeof(LocalFactor<NP>) / sizeof(double)) };
-    const double* from { reinterpret_cast<const double*>(&src) };
-    double* to { reinterpret_cast<double*>(&dst) };
-#pragma unroll 2
-    for (int i = 0; i < n; ++i) {
-        to[i] = from[i];
-    }
-}
-
 template <int NP>
 __device__ __forceinline__ void role_lists(const unsigned active,
                                            const unsigned global_mask,
@@ -123,10 +109,8 @@ static __global__ void k_reduce_slots(const double* __restrict__ partials,
 
 // sum_{r in [r0, r1)} in[r * stride + v] in ascending order.  The loads of 16
 // rows are issued together and then added one by one: a plain loop is a chain
-// of (L2 latency + add) per row.  Out of line on purpose: these launch-once,
-// run-once kernels are bound by cold instruction fetch (the sweeps stream
-// ~100 MB through L2 between two solves), so code size is what counts.
-static __device__ __noinline__ double ordered_column_sum(const double* in,
+// of (L2 latency + add) per row.
+__device__ __forceinline__ double ordered_column_sum(const double* in,
                                                      const int r0,
                                                      const int r1,
                                                      const long long stride,
@@ -135,7 +119,6 @@ static __device__ __noinline__ double ordered_column_sum(const double* in,
     constexpr int batch { 16 };
     double sum { 0.0 };
     int r { r0 };
-#pragma unroll 1
     for (; r + batch <= r1; r += batch) {
         double x[batch];
 #pragma unroll
@@ -147,7 +130,6 @@ static __device__ __noinline__ double ordered_column_sum(const double* in,
             sum += x[u];
         }
     }
-#pragma unroll 1
     for (; r < r1; ++r) {
         sum += in[static_cast<long long>(r) * stride + v];
     }
@@ -366,7 +348,7 @@ __device__ __forceinline__ void local_schur_set(const int s,
     if constexpr (NP <= 8) {
         LocalFactor<NP> F;
         local_schur_into<NP>(F, s, M, active, global_mask, dtd_local, lambda, contrib, VG);
-        copy_factor<NP>(factors[s], F);
+        factors[s] = F;
     } else {
         local_schur_into<NP>(
           factors[s], s, M, active, global_mask, dtd_local, lambda, contrib, VG);
@@ -478,7 +460,6 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
                 dtd_global[lane] = dtd;
             }
             // Row `lane` of the lower triangle of the damped, Schur-reduced matrix
-#pragma unroll 1
             for (int j = 0; j <= lane; ++j) {
                 const int o { tri_index(pg, j, lane) };
                 double v { shared_sums[o] - schur_sums[o] };
@@ -489,12 +470,10 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
             }
         }
         __syncwarp();
-#pragma unroll 1
         for (int j = 0; j < pg; ++j) {
             double v { 0.0 };
             if (row && lane >= j) {
                 v = s_L[lane][j];
-#pragma unroll 1
                 for (int k = 0; k < j; ++k) {
                     v -= s_L[lane][k] * s_L[j][k];
                 }
@@ -506,14 +485,12 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
             __syncwarp();
         }
         if (row) {
-#pragma unroll 1
             for (int j = 0; j <= lane; ++j) {
                 chol[lane * pg + j] = s_L[lane][j];
             }
         }
     } else {
         if (row) {
-#pragma unroll 1
             for (int j = 0; j <= lane; ++j) {
                 s_L[lane][j] = chol[lane * pg + j];
             }
@@ -526,7 +503,6 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
         v = which == 1 ? shared_sums[ntri + lane] - schur_sums[ntri + lane]
                        : rhs2_sums[lane] - rhs2_sums[pg + lane];
     }
-#pragma unroll 1
     for (int j = 0; j < pg; ++j) {
         const double yj { __shfl_sync(0xffffffffU, v, j) / s_L[j][j] };
         if (lane == j) {
@@ -536,7 +512,6 @@ __device__ __forceinline__ void shared_solve_warp(const int pg,
         }
     }
     // Backward substitution L' x = y
-#pragma unroll 1
     for (int i = pg - 1; i >= 0; --i) {
         const double xi { __shfl_sync(0xffffffffU, v, i) / s_L[i][i] };
         if (lane == i) {
@@ -626,8 +601,7 @@ __device__ __forceinline__ void local_backsolve_set(const int s,
                                                     double* __restrict__ delta_par)
 {
     if constexpr (NP <= 8) {
-        LocalFactor<NP> F;
-        copy_factor<NP>(F, factors[s]); // independent loads, in flight together
+        const LocalFactor<NP> F { factors[s] }; // one burst of independent loads
         local_backsolve_with<NP>(F, s, active, global_mask, delta_g, delta_par);
     } else {
         local_backsolve_with<NP>(factors[s], s, active, global_mask, delta_g, delta_par);
@@ -848,9 +822,7 @@ __device__ __forceinline__ void column_sums_own_chunks(const int cta,
     if (blocks <= 1) {
         return;
     }
-#pragma unroll 1
     for (int b0 = per_cta * cta; b0 < blocks; b0 += per_cta * kSmallCtas) {
-#pragma unroll 1
         for (int item = static_cast<int>(threadIdx.x); item < per_cta * V; item += kSmallThreads) {
             const int j { item / V };
             const int v { item - j * V };
@@ -874,7 +846,6 @@ __device__ __forceinline__ void column_sums_final(const double* in,
     const int blocks { (n_rows + kColumnChunk - 1) / kColumnChunk };
     const double* last_in { blocks > 1 ? stage : in };
     const int last_rows { blocks > 1 ? blocks : n_rows };
-#pragma unroll 1
     for (int v = static_cast<int>(threadIdx.x); v < V; v += kSmallThreads) {
         out[v] = ordered_column_sum(last_in, 0, last_rows, V, v);
     }
@@ -910,7 +881,6 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
     double* contrib_schur { a.contrib + static_cast<long long>(a.n_sets) * a.VG };
     double* stage_schur { a.stage + static_cast<long long>(chunks) * a.VG };
     if (a.prepare != 0) {
-#pragma unroll 2
         for (int i = g; i < n_par; i += cluster_threads) {
             a.par_jac[i] = a.par[i];
         }
@@ -918,7 +888,6 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
         // (dependent) index and partial loads overlap; each entry still adds
         // its slots in ascending order
         const int n_items { a.n_sets * NT };
-#pragma unroll 1
         for (int base = g; base < n_items; base += 4 * cluster_threads) {
             int first[4];
             int count[4];
@@ -936,7 +905,6 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
                 max_count = max(max_count, count[u]);
                 sum[u] = 0.0;
             }
-#pragma unroll 1
             for (int c = 0; c < max_count; ++c) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {

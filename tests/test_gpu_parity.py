@@ -271,7 +271,12 @@ def _is_accelerated(sc):
     [s for s in scenarios.ALL_SCENARIOS if not _is_accelerated(s)]
     + [dict(name="C3_small", kind="workload", workload="C3", kwargs=dict(n_sets=300, n_points=700)),
        dict(name="C5_small", kind="workload", workload="C5", kwargs=dict(n_sets=250, n_points=96)),
-       dict(name="C2_small", kind="workload", workload="C2", kwargs=dict(n_sets=5, n_points=20_000))],
+       dict(name="C2_small", kind="workload", workload="C2", kwargs=dict(n_sets=5, n_points=20_000)),
+       # 100 data sets: a partly filled CTA; 1500 and 2100: more data sets than
+       # the cluster has set-threads (1024), i.e. two and three passes
+       dict(name="C3_100", kind="workload", workload="C3", kwargs=dict(n_sets=100, n_points=200)),
+       dict(name="C3_1500", kind="workload", workload="C3", kwargs=dict(n_sets=1500, n_points=64)),
+       dict(name="C5_2100", kind="workload", workload="C5", kwargs=dict(n_sets=2100, n_points=24))],
     ids=lambda s: s["name"])
 def test_fused_small_problem_path_is_bit_identical_to_the_stagewise_path(sc, c1, monkeypatch):
     """The latency-bound regime (one GPU, <= 4096 data sets, no acceleration)
@@ -291,3 +296,30 @@ def test_fused_small_problem_path_is_bit_identical_to_the_stagewise_path(sc, c1,
     for getter in ("getJTJ", "getDTD", "getRightSide", "getLeftSide"):
         if fused["dof"] < 10_000:  # dense getters: small cases only
             np.testing.assert_array_equal(getattr(fs, getter)(), getattr(ss, getter)())
+
+
+def test_distinct_solvers_on_concurrent_host_threads(c1):
+    """SURVEY 8(b) threading row (reference doc/user_guide.tex:778): one solver
+    is not re-entrant, but distinct solvers may run concurrently from different
+    host threads.  Eight threads, each fitting its own known-answer scenario on
+    its own handle (own stream), must all reproduce the reference's values."""
+    import threading
+    todo = (scenarios.C1_SCENARIOS * 2)[:8]
+    make = backends.product_solver()
+    results, errors = [None] * len(todo), []
+
+    def work(i, sc):
+        try:
+            for _ in range(3):
+                results[i], _s = scenarios.run(sc, make, c1)
+        except Exception as e:  # noqa: BLE001
+            errors.append((sc["name"], repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i, sc)) for i, sc in enumerate(todo)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for sc, res in zip(todo, results):
+        _check_kat(sc, res, c1, tol_floor=1e-11)
