@@ -384,7 +384,9 @@ def main_b200(args, emit):
         except (OSError, KeyError, TypeError):
             traffic = None
     roofline = {
-        "bound": "fp64", "kernel": "k_jacobian",
+        # the contract's "tensor" bound: here the FP64 tensor path (DMMA m8n8k4)
+        # and the FP64 FMA pipe, which share one datapath -- not bf16
+        "bound": "tensor", "pipe": "fp64", "kernel": "k_jacobian",
         "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
         "frac": achieved_tflops / (fp64_peak / 1e12) if achieved_tflops else None,
         "peak_source": "measured live on this GPU: the higher of a register-resident DFMA loop "

@@ -18,7 +18,8 @@
 //
 // c.kronrod(...) / c.kronrod2d(...) give the fixed 15-point Kronrod panel of
 // the reference (numerical_integration.cpp:133-148,189-215);
-// c.integrate(lower, upper, f(ctx, t), rel_error) its adaptive G7/K15
+// c.integrate(lower, upper, f(ctx, t), rel_error) its adaptive G7/K15 (or, as
+// c.template integrate<PTS>(...), the Fortran version's G10/K21 ... G30/K61)
 // integrator incl. AD-valued bounds (numerical_integration.cpp:242-423);
 // c.integrate2d(y1, y2, x1, x2, f(ctx, x, y), rel_error) the direct 2-D
 // adaptive integrator (numerical_integration.cpp:426-1146).
@@ -31,10 +32,11 @@ namespace gadfit_b200 {
 
 struct QuadratureMixin
 {
-    template <class F>
+    // PTS: 15 (default), 21, 31, 41, 51 or 61 points -- c.template kronrod<21>(...)
+    template <int PTS = 15, class F>
     GADFIT_HD auto kronrod(const double lower, const double upper, F&& f) const
     {
-        return gadfit_b200::kronrod(lower, upper, f);
+        return gadfit_b200::kronrod<PTS>(lower, upper, f);
     }
     template <class F>
     GADFIT_HD auto kronrod2d(const double outer_lower,
@@ -53,14 +55,14 @@ struct ValueCtx : QuadratureMixin
     const double* p;
     GADFIT_HD explicit ValueCtx(const double* p) : p { p } {}
     GADFIT_HD ValueCtx passive() const { return *this; }
-    template <class BL, class BU, class F>
+    template <int PTS = 15, class BL, class BU, class F>
     GADFIT_HD auto integrate(const BL& lower,
                              const BU& upper,
                              F&& f,
                              const double rel_error = k_default_rel_error,
                              const double abs_error = 0.0) const
     {
-        return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+        return gadfit_b200::integrate<PTS>(*this, lower, upper, f, rel_error, abs_error);
     }
     template <class BY1, class BY2, class BX1, class BX2, class F>
     GADFIT_HD auto integrate2d(const BY1& y1,
@@ -85,14 +87,14 @@ struct GradCtx : QuadratureMixin
     const double* p;
     GADFIT_HD explicit GradCtx(const double* p) : p { p } {}
     GADFIT_HD ValueCtx passive() const { return ValueCtx { p }; }
-    template <class BL, class BU, class F>
+    template <int PTS = 15, class BL, class BU, class F>
     GADFIT_HD auto integrate(const BL& lower,
                              const BU& upper,
                              F&& f,
                              const double rel_error = k_default_rel_error,
                              const double abs_error = 0.0) const
     {
-        return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+        return gadfit_b200::integrate<PTS>(*this, lower, upper, f, rel_error, abs_error);
     }
     template <class BY1, class BY2, class BX1, class BX2, class F>
     GADFIT_HD auto integrate2d(const BY1& y1,
@@ -123,14 +125,14 @@ struct Dir2Ctx : QuadratureMixin
     GADFIT_HD Dir2Ctx(const double* p, const double* seed) : p { p }, seed { seed }
     {}
     GADFIT_HD ValueCtx passive() const { return ValueCtx { p }; }
-    template <class BL, class BU, class F>
+    template <int PTS = 15, class BL, class BU, class F>
     GADFIT_HD auto integrate(const BL& lower,
                              const BU& upper,
                              F&& f,
                              const double rel_error = k_default_rel_error,
                              const double abs_error = 0.0) const
     {
-        return gadfit_b200::integrate(*this, lower, upper, f, rel_error, abs_error);
+        return gadfit_b200::integrate<PTS>(*this, lower, upper, f, rel_error, abs_error);
     }
     template <class BY1, class BY2, class BX1, class BX2, class F>
     GADFIT_HD auto integrate2d(const BY1& y1,

@@ -77,20 +77,6 @@ GADFIT_HD double k15_weight(const int i)
 #endif
 }
 
-// numerical_integration.cpp:133-148
-template <class F>
-GADFIT_HD auto kronrod(const double lower, const double upper, F&& f)
-{
-    const double scale { (upper - lower) / 2 };
-    const double shift { (lower + upper) / 2 };
-    auto sum { k15_weight(0) * f(Passive { scale * k15_root(0) + shift }) };
-#pragma unroll 1
-    for (int i = 1; i < k15_size; ++i) {
-        sum = sum + k15_weight(i) * f(Passive { scale * k15_root(i) + shift });
-    }
-    return scale * sum;
-}
-
 // numerical_integration.cpp:189-215.  f(arg_x, arg_y): arg_x runs over the
 // inner bounds in the OUTER loop, arg_y over the outer bounds in the inner
 // loop, exactly as the reference does.
@@ -167,24 +153,88 @@ GADFIT_HD double g7_weight(const int i)
 #endif
 }
 
+// ---------------------------------------------------------------------------
+// Rule traits.  KronrodRule<15> is the rule of the C++ reference; the Fortran
+// version also offers 21, 31, 41, 51 and 61 points (set_integration_rule,
+// fortran/gadfit/numerical_integration.F90:139-171) -- quadrature_rules.h.
+// A rule is a template argument here (`c.template integrate<31>(...)`,
+// `kronrod<21>(...)`): the node loop bound is a compile-time constant and the
+// tables sit in the constant bank.  Every rule lists its nodes in the order of
+// the reference's tables; the Gauss nodes are the odd positions.
+// ---------------------------------------------------------------------------
+template <int PTS>
+struct KronrodRule;
+
+template <>
+struct KronrodRule<15>
+{
+    static constexpr int size { k15_size };
+    GADFIT_HD static double root(const int i) { return k15_root(i); }
+    GADFIT_HD static double weight(const int i) { return k15_weight(i); }
+    GADFIT_HD static double gauss_weight(const int i) { return g7_weight(i); }
+};
+
+#define GADFIT_LIST(...) __VA_ARGS__
+#if defined(__CUDACC__)
+#define GADFIT_RULE_DEVICE_TABLE(name, n, ...) static __constant__ double name##_dev[n] { __VA_ARGS__ };
+#else
+#define GADFIT_RULE_DEVICE_TABLE(name, n, ...)
+#endif
+#if defined(__CUDA_ARCH__)
+#define GADFIT_RULE_ENTRY(name, i) name##_dev[i]
+#else
+#define GADFIT_RULE_ENTRY(name, i) name##_host[i]
+#endif
+#define GADFIT_DEFINE_KRONROD_RULE(PTS, NG, ROOTS, KRONROD, GAUSS)                          \
+    GADFIT_RULE_DEVICE_TABLE(k##PTS##_roots, PTS, ROOTS)                                    \
+    GADFIT_RULE_DEVICE_TABLE(k##PTS##_weights, PTS, KRONROD)                                \
+    GADFIT_RULE_DEVICE_TABLE(k##PTS##_gauss, NG, GAUSS)                                     \
+    static constexpr double k##PTS##_roots_host[PTS] { ROOTS };                             \
+    static constexpr double k##PTS##_weights_host[PTS] { KRONROD };                         \
+    static constexpr double k##PTS##_gauss_host[NG] { GAUSS };                              \
+    template <>                                                                             \
+    struct KronrodRule<PTS>                                                                 \
+    {                                                                                       \
+        static constexpr int size { PTS };                                                  \
+        GADFIT_HD static double root(const int i) { return GADFIT_RULE_ENTRY(k##PTS##_roots, i); }      \
+        GADFIT_HD static double weight(const int i) { return GADFIT_RULE_ENTRY(k##PTS##_weights, i); }  \
+        GADFIT_HD static double gauss_weight(const int i) { return GADFIT_RULE_ENTRY(k##PTS##_gauss, i); } \
+    };
+
+// numerical_integration.cpp:133-148 (any rule)
+template <int PTS = 15, class F>
+GADFIT_HD auto kronrod(const double lower, const double upper, F&& f)
+{
+    using Rule = KronrodRule<PTS>;
+    const double scale { (upper - lower) / 2 };
+    const double shift { (lower + upper) / 2 };
+    auto sum { Rule::weight(0) * f(Passive { scale * Rule::root(0) + shift }) };
+#pragma unroll 1
+    for (int i = 1; i < Rule::size; ++i) {
+        sum = sum + Rule::weight(i) * f(Passive { scale * Rule::root(i) + shift });
+    }
+    return scale * sum;
+}
+
 // numerical_integration.cpp:108-131: K15 value and |K15 - G7| of one panel
-template <class Ctx, class F>
+template <int PTS = 15, class Ctx, class F>
 GADFIT_HD double gauss_kronrod(const Ctx& passive_ctx,
                                F&& f,
                                const double lower,
                                const double upper,
                                double& abs_error)
 {
+    using Rule = KronrodRule<PTS>;
     const double scale { (upper - lower) / 2 };
     const double shift { (lower + upper) / 2 };
     double sum_kronrod { 0.0 };
     double sum_gauss { 0.0 };
 #pragma unroll 1
-    for (int i = 0; i < k15_size; ++i) {
-        const double val { value_of(f(passive_ctx, Passive { scale * k15_root(i) + shift })) };
-        sum_kronrod += k15_weight(i) * val;
+    for (int i = 0; i < Rule::size; ++i) {
+        const double val { value_of(f(passive_ctx, Passive { scale * Rule::root(i) + shift })) };
+        sum_kronrod += Rule::weight(i) * val;
         if (i % 2 == 1) {
-            sum_gauss += g7_weight(i / 2) * val;
+            sum_gauss += Rule::gauss_weight(i / 2) * val;
         }
     }
     sum_kronrod *= scale;
@@ -229,7 +279,7 @@ GADFIT_HD auto leibniz(const Ctx& c, F&& f, const R& result, const B& bound, con
     }
 }
 
-template <class Ctx, class F, class BL, class BU>
+template <int PTS = 15, class Ctx, class F, class BL, class BU>
 GADFIT_HD auto integrate(const Ctx& c,
                          const BL& lower_bound,
                          const BU& upper_bound,
@@ -246,7 +296,7 @@ GADFIT_HD auto integrate(const Ctx& c,
     double errs[k_max_panels];
     lo[0] = lower;
     hi[0] = upper;
-    sums[0] = gauss_kronrod(pc, f, lower, upper, errs[0]);
+    sums[0] = gauss_kronrod<PTS>(pc, f, lower, upper, errs[0]);
     int n_panels { 0 };
     for (int iter = 0; iter + 1 < k_max_panels; ++iter) {
         // first panel with the largest error (std::max_element)
@@ -259,8 +309,8 @@ GADFIT_HD auto integrate(const Ctx& c,
         const double a { lo[worst] };
         const double b { hi[worst] };
         const double middle { (b + a) / 2 };
-        sums[worst] = gauss_kronrod(pc, f, a, middle, errs[worst]);
-        sums[iter + 1] = gauss_kronrod(pc, f, middle, b, errs[iter + 1]);
+        sums[worst] = gauss_kronrod<PTS>(pc, f, a, middle, errs[worst]);
+        sums[iter + 1] = gauss_kronrod<PTS>(pc, f, middle, b, errs[iter + 1]);
         hi[worst] = middle;
         lo[iter + 1] = middle;
         hi[iter + 1] = b;
@@ -276,9 +326,9 @@ GADFIT_HD auto integrate(const Ctx& c,
         }
     }
     // Final pass with AD on (:292-298); the sum starts from a passive zero
-    auto result { Passive { 0.0 } + kronrod(lo[0], hi[0], [&](const Passive& t) { return f(c, t); }) };
+    auto result { Passive { 0.0 } + kronrod<PTS>(lo[0], hi[0], [&](const Passive& t) { return f(c, t); }) };
     for (int i = 1; i < n_panels; ++i) {
-        result = result + kronrod(lo[i], hi[i], [&](const Passive& t) { return f(c, t); });
+        result = result + kronrod<PTS>(lo[i], hi[i], [&](const Passive& t) { return f(c, t); });
     }
     if (n_panels == 0) {
         // workspace exhausted: poison the value (=> the step is rejected)
@@ -476,3 +526,5 @@ GADFIT_HD auto integrate2d(const Ctx& c,
 }
 
 } // namespace gadfit_b200
+
+#include "quadrature_rules.h"

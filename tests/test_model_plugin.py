@@ -37,6 +37,7 @@ def test_plugin_registers_its_functions_without_a_gpu(user_plugin):
     registered = g.models()
     assert registered["user_decay"] == 3
     assert registered["user_stretched_integral"] == 4
+    assert all(registered[f"user_stretched_integral_k{p}"] == 4 for p in (21, 31, 41, 51, 61))
     g.load_models(user_plugin)  # loading twice is a no-op
     assert list(g.models()).count("user_decay") == 1
     s = g.LMsolver("user_decay")  # host-side bookkeeping works without a device
@@ -95,6 +96,39 @@ def test_user_function_with_adaptive_integral_recovers_its_parameters(user_plugi
     assert s.chi2() < 1e-14
     np.testing.assert_allclose(s.getValue(3.0), truth[0] * quad(
         lambda t: np.exp(-(t / truth[1]) ** truth[2]), 0.0, 3.0)[0] + truth[3], rtol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pts", (21, 31, 41, 51, 61))
+def test_other_gauss_kronrod_rules_on_the_device(user_plugin, pts):
+    """The Fortran version's integration rules (set_integration_rule) as a
+    template argument of c.integrate: the same fit as with the default 15-point
+    rule -- every rule integrates adaptively to 1e-10, so the fitted parameters
+    agree far below the data's information content."""
+    truth = (2.0, 1.5, 0.8, 0.3)
+    rng = np.random.default_rng(7)
+    x = np.linspace(0.2, 6.0, 120)
+    from scipy.integrate import quad
+    y = np.array([truth[0] * quad(lambda t: np.exp(-(t / truth[1]) ** truth[2]), 0.0, xi,
+                                  epsabs=1e-13, epsrel=1e-13)[0] + truth[3] for xi in x])
+    y = y + 1e-3 * rng.standard_normal(x.size)
+
+    def fit(model):
+        s = g.LMsolver(model)
+        s.addDataset(x, y)
+        for k, v in enumerate((1.5, 1.2, 1.0, 0.1)):
+            s.setPar(k, v, True)
+        s.settings.iteration_limit = 12
+        s.settings.acceleration_threshold = 0.9  # omega sweep: second order through the rule
+        s.fit(1.0)
+        return np.array([s.getParValue(k) for k in range(4)] + [s.chi2()]), s.trace()
+
+    want, want_trace = fit("user_stretched_integral")
+    got, got_trace = fit(f"user_stretched_integral_k{pts}")
+    np.testing.assert_allclose(got, want, rtol=1e-8)
+    # identical decisions until chi2 has converged (afterwards accept / reject
+    # is decided by the last bits, cf. c++/tests/lm_solver.cpp:396-398)
+    assert [t["decision"] for t in got_trace[:8]] == [t["decision"] for t in want_trace[:8]]
 
 
 # ---- fitting functions defined from Python (gadfit_b200.define_model) -------

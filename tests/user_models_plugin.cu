@@ -37,3 +37,31 @@ struct UserStretched
     }
 };
 GADFIT_B200_REGISTER_MODEL(UserStretched)
+
+// The same function with the Fortran version's other Gauss-Kronrod rules
+// (set_integration_rule, fortran/gadfit/numerical_integration.F90:139-171):
+// the rule is a template argument of c.integrate
+template <int PTS>
+struct UserStretchedRule
+{
+    static constexpr int n_pars { 4 };
+    static constexpr const char* name { PTS == 21   ? "user_stretched_integral_k21"
+                                        : PTS == 31 ? "user_stretched_integral_k31"
+                                        : PTS == 41 ? "user_stretched_integral_k41"
+                                        : PTS == 51 ? "user_stretched_integral_k51"
+                                                    : "user_stretched_integral_k61" };
+    template <class Ctx>
+    GADFIT_HD auto operator()(const Ctx& c, const double x) const
+    {
+        using namespace gadfit_b200;
+        const auto integrand { [](const auto& cc, const auto& t) {
+            return exp(-pow(t / par<1>(cc), par<2>(cc)));
+        } };
+        return par<0>(c) * c.template integrate<PTS>(0.0, x, integrand, 1e-10) + par<3>(c);
+    }
+};
+GADFIT_B200_REGISTER_MODEL(UserStretchedRule<21>)
+GADFIT_B200_REGISTER_MODEL(UserStretchedRule<31>)
+GADFIT_B200_REGISTER_MODEL(UserStretchedRule<41>)
+GADFIT_B200_REGISTER_MODEL(UserStretchedRule<51>)
+GADFIT_B200_REGISTER_MODEL(UserStretchedRule<61>)
