@@ -55,10 +55,15 @@ def launches(tag):
         name = r[ki].split("(")[0][:70]
         agg[name][0] += 1
         agg[name][1] += v
-    solver = {k: v for k, v in agg.items() if "k_dfma" not in k}
+    # k_dfma / k_dmma are bench.py's FP64 peak micro-benchmarks (csrc/microbench.cu),
+    # launched before the timed region: not part of the step
+    micro = {k: v for k, v in agg.items() if "k_dfma" in k or "k_dmma" in k}
+    solver = {k: v for k, v in agg.items() if k not in micro}
     total = sum(v for _, v in solver.values())
     lines = [f"# ncu launch list, `bench.py --steps 2 --warmup 1 --repeats 1` on C2 ({tag})", "",
-             "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.", "",
+             "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.",
+             "Not listed: the FP64 peak micro-benchmarks bench.py runs before the timed region ("
+             + ", ".join(f"`{k.split('::')[-1]}` x {n}" for k, (n, _) in micro.items()) + ").", "",
              "| kernel | launches | total us | share of solver kernels |", "|---|---|---|---|"]
     table = {}
     for k, (n, v) in sorted(solver.items(), key=lambda kv: -kv[1][1]):
