@@ -193,7 +193,10 @@ contains
 
   ! gadfit.F90:133-184.  Only f and num_datasets have a meaning here; the AD
   ! tape and integration workspace sizes of the reference have no counterpart
-  ! (registers / fixed-order quadrature).
+  ! (registers / per-thread panel stacks).  integration_rule: the rule is part
+  ! of the compiled fitting function (c.template integrate<PTS>(...), PTS = 15,
+  ! 21, 31, 41, 51 or 61, include/gadfit_b200/quadrature.h), so the argument is
+  ! accepted for source compatibility and not used.
   subroutine gadf_init(f, num_datasets, sweep_size, trace_size, const_size, &
        & ws_size, ws_size_inner, integration_rule, ad_memory, &
        & rel_error_inner, rel_error)
