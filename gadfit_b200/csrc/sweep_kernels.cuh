@@ -203,10 +203,28 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
     constexpr int kChi2Unroll { Chi2Tuning<Model>::unroll };
     __shared__ double s_par[NP];
     __shared__ double s_red[kThreads / 32];
-    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
-                                    / gridDim.x) };
-    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
-                                    * (blockIdx.x + 1) / gridDim.x) };
+    // Contiguous tile range of this CTA.  With kChi2Unroll > 1 the cut points
+    // are moved up to the next multiple of kChi2Unroll tiles counted from the
+    // start of the data set they fall into (or to its end): a range then never
+    // starts or stops in the middle of an unrolled group, which would leave up
+    // to 2 (kChi2Unroll - 1) tiles per CTA to the one-tile-at-a-time path
+    // (config 3: 54 tiles per CTA, 16 per data set).
+    const auto first_tile { [&](const int b) -> int {
+        if (b >= static_cast<int>(gridDim.x)) {
+            return a.n_tiles;
+        }
+        int t { static_cast<int>(static_cast<long long>(a.n_tiles) * b / gridDim.x) };
+        if (kChi2Unroll > 1 && b > 0) {
+            TileWalker w {};
+            w.seek(a, t);
+            w.advance_to(a, t);
+            const int groups { (t - w.tile_begin + kChi2Unroll - 1) / kChi2Unroll };
+            t = min(w.tile_begin + groups * kChi2Unroll, w.tile_end);
+        }
+        return t;
+    } };
+    const int t0 { first_tile(static_cast<int>(blockIdx.x)) };
+    const int t1 { first_tile(static_cast<int>(blockIdx.x) + 1) };
     double sum { 0.0 };
     const int tid { static_cast<int>(threadIdx.x) };
     TileWalker walk {};
