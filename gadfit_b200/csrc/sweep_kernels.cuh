@@ -244,39 +244,55 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
             cur_set = walk.set;
         }
         const long long base { walk.off(t) + tid };
-        if (t + kChi2Unroll <= t1 && t + kChi2Unroll <= walk.tile_end) {
-            // kChi2Unroll consecutive tiles of one data set (contiguous in
-            // memory; only the last may be partial): the loads are issued
-            // together and the unrolled evaluations share every
-            // parameter-only subexpression (1/w, ...) and constant
-            const int last_len { walk.len(t + kChi2Unroll - 1) };
-            double x[kChi2Unroll];
-            double y[kChi2Unroll];
-            double sg[kChi2Unroll];
+        // W consecutive tiles of one data set (contiguous in memory; only the
+        // last may be partial): the loads are issued together and the unrolled
+        // evaluations share every parameter-only subexpression (1/w, ...) and
+        // constant.  Groups of kChi2Unroll tiles, then 4, 2, 1 for what is
+        // left of the data set; a thread adds its terms in ascending tile
+        // order whatever the grouping, so the sum does not depend on it.
+        const int avail { min(t1, walk.tile_end) - t };
+        const auto group { [&](auto width) {
+            constexpr int W { decltype(width)::value };
+            const int last_len { walk.len(t + W - 1) };
+            if constexpr (W == 1) {
+                // threads past the end of the data set evaluate nothing
+                if (tid < last_len) {
+                    const double f { value_of(Model {}(ValueCtx { s_par }, a.x[base])) };
+                    const double diff { (a.y[base] - f) / a.sig[base] };
+                    sum += diff * diff;
+                }
+                ++t;
+                return;
+            }
+            double x[W];
+            double y[W];
+            double sg[W];
 #pragma unroll
-            for (int u = 0; u < kChi2Unroll; ++u) {
-                const bool in { u + 1 < kChi2Unroll || tid < last_len };
+            for (int u = 0; u < W; ++u) {
+                const bool in { u + 1 < W || tid < last_len };
                 const long long i { base + u * kTile };
                 x[u] = in ? a.x[i] : 0.0;
                 y[u] = in ? a.y[i] : 0.0;
                 sg[u] = in ? a.sig[i] : 1.0;
             }
 #pragma unroll
-            for (int u = 0; u < kChi2Unroll; ++u) {
+            for (int u = 0; u < W; ++u) {
                 const double f { value_of(Model {}(ValueCtx { s_par }, x[u])) };
                 const double diff { (y[u] - f) / sg[u] };
-                if (u + 1 < kChi2Unroll || tid < last_len) {
+                if (u + 1 < W || tid < last_len) {
                     sum += diff * diff;
                 }
             }
-            t += kChi2Unroll;
+            t += W;
+        } };
+        if (kChi2Unroll > 4 && avail >= kChi2Unroll) {
+            group(std::integral_constant<int, kChi2Unroll> {});
+        } else if (kChi2Unroll >= 4 && avail >= 4) {
+            group(std::integral_constant<int, 4> {});
+        } else if (kChi2Unroll >= 2 && avail >= 2) {
+            group(std::integral_constant<int, 2> {});
         } else {
-            if (tid < walk.len(t)) {
-                const double f { value_of(Model {}(ValueCtx { s_par }, a.x[base])) };
-                const double diff { (a.y[base] - f) / a.sig[base] };
-                sum += diff * diff;
-            }
-            ++t;
+            group(std::integral_constant<int, 1> {});
         }
     }
     const double total { block_sum(sum, s_red) };
