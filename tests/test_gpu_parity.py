@@ -272,14 +272,14 @@ def _is_accelerated(sc):
     + [dict(name="C3_small", kind="workload", workload="C3", kwargs=dict(n_sets=300, n_points=700)),
        dict(name="C5_small", kind="workload", workload="C5", kwargs=dict(n_sets=250, n_points=96)),
        dict(name="C2_small", kind="workload", workload="C2", kwargs=dict(n_sets=5, n_points=20_000)),
-       # 100 data sets: a partly filled CTA; 1500 and 2100: more data sets than
-       # the cluster has set-threads (1024), i.e. two and three passes
+       # 100 data sets: a partly filled CTA; 1500 and 2048: more data sets than
+       # the cluster has set-threads (1024), i.e. two passes (2048 = the limit)
        dict(name="C3_100", kind="workload", workload="C3", kwargs=dict(n_sets=100, n_points=200)),
        dict(name="C3_1500", kind="workload", workload="C3", kwargs=dict(n_sets=1500, n_points=64)),
-       dict(name="C5_2100", kind="workload", workload="C5", kwargs=dict(n_sets=2100, n_points=24))],
+       dict(name="C5_2048", kind="workload", workload="C5", kwargs=dict(n_sets=2048, n_points=24))],
     ids=lambda s: s["name"])
 def test_fused_small_problem_path_is_bit_identical_to_the_stagewise_path(sc, c1, monkeypatch):
-    """The latency-bound regime (one GPU, <= 4096 data sets, no acceleration)
+    """The latency-bound regime (one GPU, <= 2048 data sets, no acceleration)
     runs a trial step as 4 launches (k_solve_small / k_finish_trial) instead of
     16.  Same per-data-set code, same summation order: every trial record and
     every parameter must be identical to the last bit, with fewer launches."""
