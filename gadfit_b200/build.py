@@ -140,6 +140,27 @@ def build_test_models(force: bool = False, verbose: bool = False) -> str:
     return _compile_and_link(units, TEST_MODELS_OUT, force, verbose, None, [], lineinfo=False)
 
 
+DEVICE_CHECKS_OUT = os.path.join(ROOT, "tests", "_build", "libdevice_dual_check.so")
+
+
+def build_device_checks(force: bool = False) -> str:
+    """tests/_build/libdevice_dual_check.so (test infrastructure): the
+    reference's AD known-answer expressions evaluated in a kernel,
+    tests/device_dual_check.cu."""
+    src = os.path.join(ROOT, "tests", "device_dual_check.cu")
+    deps = [src, os.path.join(ROOT, "tests", "dual_check_expr.h"),
+            os.path.join(ROOT, "include", "gadfit_b200", "dual.h")]
+    if not force and not _stale(DEVICE_CHECKS_OUT, deps):
+        return DEVICE_CHECKS_OUT
+    os.makedirs(os.path.dirname(DEVICE_CHECKS_OUT), exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests"), src, "-o", DEVICE_CHECKS_OUT]
+    r = subprocess.run(cmd, env=_env(), capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return DEVICE_CHECKS_OUT
+
+
 if __name__ == "__main__":
     if "--plugin" in sys.argv:
         # python -m gadfit_b200.build --plugin a.cu [b.cu ...] -o libmy_models.so
