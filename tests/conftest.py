@@ -25,3 +25,32 @@ def c1():
 @pytest.fixture(scope="session")
 def golden():
     return json.load(open(os.path.join(ROOT, "tests", "golden", "golden_ref.json")))
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Which tolerance every trace / parameter comparison of this session met
+    (tests/scenarios.py: compare_to_golden)."""
+    import scenarios
+    log = scenarios.PARITY_LOG
+    if not log:
+        return
+    tr = terminalreporter
+    tr.section("parity of accept/reject traces and parameters")
+    relaxed = [r for r in log if r["needed_relaxed"]]
+    to_end = sum(r["trace_identical_to_end"] for r in log)
+    tr.write_line(f"{len(log)} comparisons: {to_end} with a trace identical to the last trial, "
+                  f"{len(log) - len(relaxed)} with parameters within {scenarios.STRICT_PAR_TOL:g}, "
+                  f"{len(relaxed)} needed the post-convergence tolerance {scenarios.RELAXED_PAR_TOL:g}")
+    worst = max(log, key=lambda r: r["worst_parameter_error"])
+    tr.write_line(f"worst parameter error {worst['worst_parameter_error']:.2e} ({worst['name']} {worst['label']}), "
+                  f"worst chi2 error {max(r['chi2_error'] for r in log):.2e}")
+    for r in log:
+        if r["needed_relaxed"] or not r["trace_identical_to_end"]:
+            tr.write_line(
+                f"  {r['name']:<34} {r['label']:<8} trials {r['trials_identical']}/{r['trials']} identical "
+                f"(compared {r['trials_compared']}), parameters {r['worst_parameter_error']:.1e} "
+                f"<= {r['parameter_tolerance']:g}" + ("  RELAXED" if r["needed_relaxed"] else ""))
+    out = os.environ.get("GADFIT_PARITY_LOG")
+    if out:
+        with open(out, "w") as f:
+            json.dump(log, f, indent=1)

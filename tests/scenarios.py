@@ -337,36 +337,92 @@ def run(scenario: dict, make_solver, c1_data: dict, n_threads: int = 1) -> dict:
     ), s
 
 
-def compare_to_golden(got: dict, want: dict, rtol: float, converged_rel: float = 1e-12):
-    """Parameters and chi2 within rtol; accept/reject sequence identical up to
-    the trial where chi2 has converged to `converged_rel` (beyond that the
-    reference's own decisions are rounding noise, cf. its test comment at
-    c++/tests/lm_solver.cpp:396-398).  Returns the number of trials compared."""
+# One record per compare_to_golden() call of this test session; printed by
+# tests/conftest.py at the end of the run and checked by
+# tests/test_zz_parity_budget.py (how many comparisons NEEDED the relaxed
+# parameter tolerance).
+PARITY_LOG: list = []
+STRICT_PAR_TOL = 1e-10   # north star: parameters and chi2 to 1e-10 relative
+RELAXED_PAR_TOL = 1e-7   # only after chi2 has converged to rounding noise
+
+
+class ParityResult(int):
+    """Number of trials compared (an int, for the callers' `n >= 3` checks) +
+    the record of what was compared and at which tolerance."""
+    record: dict
+
+
+def _par_error(gp, wp):
+    """Largest |got - want| relative to |want|, with an absolute floor of 1e-11
+    of the largest magnitude the parameter takes over the data sets: a local
+    parameter that happens to sit near zero in one data set (e.g. a background
+    slope of 2e-3) has no meaningful relative error."""
+    floor = 1e-11 * np.max(np.abs(wp), axis=0, keepdims=True)
+    excess = np.abs(gp - wp) - floor
+    return float(np.max(np.maximum(excess, 0.0) / np.maximum(np.abs(wp), 1e-300)))
+
+
+def compare_to_golden(got: dict, want: dict, rtol: float, converged_rel: float = 1e-12,
+                      label: str = ""):
+    """chi2 and the accept/reject sequence of `got` against `want`:
+
+    * every trial up to and including the first one whose chi2 change is
+      <= `converged_rel` relative must have the same decision, the same lambda
+      and new_chi2 within rtol.  Beyond that point the reference's own
+      decisions are rounding noise (its test comment,
+      c++/tests/lm_solver.cpp:396-398); if no such trial exists the whole trace
+      and the iteration count must be identical;
+    * final chi2 within max(rtol, 1e-12);
+    * parameters within max(rtol, 1e-10) (STRICT, the north star's tolerance).
+      Only if the trace comparison stopped at a converged trial AND the strict
+      check fails, 1e-7 is accepted (the remaining iterations move the
+      parameters by rounding noise times the conditioning) -- and the record
+      says so: `needed_relaxed`.  tests/test_zz_parity_budget.py bounds how
+      many comparisons of a session may need that.
+
+    Returns the number of trials compared (ParityResult, an int with a
+    `.record`)."""
     tg, tw = got["trace"], want["trace"]
     n_cmp = 0
+    stopped_at_convergence = False
     for a, b in zip(tg, tw):
         assert a["decision"] == b["decision"], (got["name"], n_cmp, a, b)
         assert a["lambda_"] == b["lambda_"], (got["name"], n_cmp, a, b)
         np.testing.assert_allclose(a["new_chi2"], b["new_chi2"], rtol=rtol)
         n_cmp += 1
         if abs(b["new_chi2"] - b["old_chi2"]) <= converged_rel * abs(b["old_chi2"]):
+            stopped_at_convergence = n_cmp < len(tw)
             break
     else:
         assert len(tg) == len(tw), (got["name"], len(tg), len(tw))
         assert got["iterations"] == want["iterations"]
-    converged = n_cmp < len(tw)
-    # after convergence the remaining iterations only move the parameters by
-    # rounding noise times the conditioning: compare at a looser tolerance
-    # Stated tolerance of the north star: parameters and chi2 to 1e-10 relative
-    tol = max(rtol, 1e-10) if not converged else max(rtol, 1e-7)
+    # how far the two traces agree in fact (decisions and lambda), for the record
+    n_same = 0
+    for a, b in zip(tg, tw):
+        if a["decision"] != b["decision"] or a["lambda_"] != b["lambda_"]:
+            break
+        n_same += 1
+    identical_to_end = n_same == len(tw) == len(tg) and got["iterations"] == want["iterations"]
     np.testing.assert_allclose(got["chi2"], want["chi2"], rtol=max(rtol, 1e-12))
-    # A local parameter that happens to sit near zero in one data set (e.g. a
-    # background slope of 2e-3) has no meaningful relative error: the absolute
-    # floor is 1e-11 of the largest magnitude that parameter takes over the
-    # data sets.
     gp, wp = np.array(got["pars"]), np.array(want["pars"])
-    floor = 1e-11 * np.max(np.abs(wp), axis=0, keepdims=True)
-    assert np.all(np.abs(gp - wp) <= tol * np.abs(wp) + floor), (
-        got["name"], float(np.max(np.abs(gp - wp) / np.maximum(np.abs(wp), 1e-300))))
+    worst = _par_error(gp, wp)
+    strict = max(rtol, STRICT_PAR_TOL)
+    needed_relaxed = False
+    if worst > strict:
+        # the relaxed tolerance exists only for the post-convergence tail
+        assert stopped_at_convergence and not identical_to_end, (
+            got["name"], "parameters differ by", worst, "with an identical trace: tolerance", strict)
+        assert worst <= max(rtol, RELAXED_PAR_TOL), (got["name"], worst)
+        needed_relaxed = True
     assert got["dof"] == want["dof"]
-    return n_cmp
+    chi2_rel = abs(got["chi2"] - want["chi2"]) / max(abs(want["chi2"]), 1e-300)
+    result = ParityResult(n_cmp)
+    result.record = dict(
+        name=got["name"], label=label, trials=len(tw), trials_compared=n_cmp,
+        trials_identical=n_same, trace_identical_to_end=bool(identical_to_end),
+        stopped_at_converged_trial=bool(stopped_at_convergence),
+        worst_parameter_error=worst, chi2_error=chi2_rel,
+        parameter_tolerance=RELAXED_PAR_TOL if needed_relaxed else strict,
+        needed_relaxed=needed_relaxed)
+    PARITY_LOG.append(result.record)
+    return result

@@ -27,7 +27,7 @@ def test_golden_reference_runs(sc, c1, golden):
     """chi2, parameters, iteration count and the accept/reject trace of the
     unmodified reference (tests/golden/golden_ref.json)."""
     res, _ = scenarios.run(sc, backends.product_solver(), c1)
-    n = scenarios.compare_to_golden(res, golden["scenarios"][sc["name"]], rtol=1e-10)
+    n = scenarios.compare_to_golden(res, golden["scenarios"][sc["name"]], rtol=1e-10, label="device")
     assert n >= min(3, len(golden["scenarios"][sc["name"]]["trace"]))
 
 
@@ -88,7 +88,7 @@ def test_against_block_arrow_oracle_at_sizes_the_reference_cannot_run(name, kwar
     sc = dict(name=name, kind="workload", workload=name, kwargs=kwargs)
     got, gs = scenarios.run(sc, backends.product_solver(), c1)
     want, _ = scenarios.run(sc, backends.oracle_solver(2), c1, n_threads=8)
-    n = scenarios.compare_to_golden(got, want, rtol=1e-10)
+    n = scenarios.compare_to_golden(got, want, rtol=1e-10, label="device-vs-oracle")
     assert n >= 3
     assert gs.launches() > 0
 

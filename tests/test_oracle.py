@@ -40,7 +40,8 @@ def test_oracle_reproduces_reference_known_answers(sc, mode, c1):
 @pytest.mark.parametrize("mode", [1, 2], ids=["dense", "block_arrow"])
 def test_oracle_matches_golden_reference_runs(sc, mode, c1, golden):
     res, _ = scenarios.run(sc, backends.oracle_solver(mode), c1)
-    n = scenarios.compare_to_golden(res, golden["scenarios"][sc["name"]], rtol=1e-11)
+    n = scenarios.compare_to_golden(res, golden["scenarios"][sc["name"]], rtol=1e-11,
+                                    label="oracle-" + ("dense" if mode == 1 else "block"))
     assert n >= min(3, len(golden["scenarios"][sc["name"]]["trace"]))
 
 

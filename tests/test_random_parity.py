@@ -109,10 +109,10 @@ def test_oracle_matches_compiled_reference_on_random_setups(seed):
     got = run_case(case, backends.oracle_solver(1))
     assert usable(want) == usable(got)
     if usable(want):
-        scenarios.compare_to_golden(got, want, rtol=1e-10)
+        scenarios.compare_to_golden(got, want, rtol=1e-10, label="oracle-dense")
     got_block = run_case(case, backends.oracle_solver(2))  # block-arrow solve
     if usable(want):
-        scenarios.compare_to_golden(got_block, want, rtol=1e-10)
+        scenarios.compare_to_golden(got_block, want, rtol=1e-10, label="oracle-block")
 
 
 @pytest.mark.gpu
@@ -123,4 +123,4 @@ def test_device_matches_oracle_on_random_setups(seed):
     got = run_case(case, backends.product_solver())
     assert usable(want) == usable(got)
     if usable(want):
-        scenarios.compare_to_golden(got, want, rtol=1e-10)
+        scenarios.compare_to_golden(got, want, rtol=1e-10, label="device-vs-oracle")
