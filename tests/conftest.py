@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+    config.addinivalue_line("markers", "slow: full-size runs of the CPU reference beside the GPU (about a minute)")
 
 
 @pytest.fixture(scope="session")

@@ -201,20 +201,48 @@ def _consistency_checks(s, n_iterations):
     np.testing.assert_allclose(s.chi2(), acc[-1]["new_chi2"], rtol=1e-13)
 
 
+def _host_threads():
+    import os
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
+@pytest.mark.parametrize("name,kwargs,what", [
+    # BASELINE config 3 at FULL size, BASELINE's own settings (10 iterations):
+    # n = 4002 columns, which the dense reference cannot run
+    ("C3", dict(iteration_limit=10), "full size 1000 x 4096"),
+    # BASELINE config 4, full-size data sets (65 536 points, geodesic
+    # acceleration, 8 iterations), a quarter of the data sets: n = 131 columns
+    ("C4", dict(n_sets=64, n_points=65536, iteration_limit=8), "64 x 65536"),
+    # BASELINE config 5, full-size data sets, 2000 of them: n = 6004 columns
+    ("C5", dict(n_sets=2000, n_points=256, iteration_limit=6), "2000 x 256"),
+], ids=["C3_full", "C4_64x65536", "C5_2000x256"])
+def test_baseline_shapes_against_the_block_arrow_oracle(name, kwargs, what, c1):
+    """The BASELINE shapes at (or near) full size against the CPU restatement
+    in block-arrow mode on all host threads (seconds to a minute): identical
+    accept/reject sequence and lambda, chi2 and EVERY parameter of every data
+    set to 1e-10 -- not invariants."""
+    sc = dict(name=f"{name}_{what.replace(' ', '')}", kind="workload", workload=name, kwargs=kwargs)
+    got, gs = scenarios.run(sc, backends.product_solver(), c1)
+    want, _ = scenarios.run(sc, backends.oracle_solver(2), c1, n_threads=_host_threads())
+    n = scenarios.compare_to_golden(got, want, rtol=1e-10, label="device-vs-oracle")
+    assert n >= 3
+    assert n.record["trials_identical"] == len(want["trace"]), n.record
+    assert gs.launches() > 0
+
+
 def test_full_size_c4_single_integral_with_acceleration(c1):
     """BASELINE config 4 at FULL size (256 x 65 536 points, fixed 15-node
-    Kronrod panel per point, geodesic acceleration): invariants, and the shared
-    parameters of a 16-data-set subset fitted by the block-arrow oracle agree
-    with the same subset on the GPU (the full problem is out of CPU reach)."""
+    Kronrod panel per point, geodesic acceleration), which no CPU oracle
+    finishes in test time: invariants, and the first 64 data sets' problem
+    is the one test_baseline_shapes_against_the_block_arrow_oracle pins to
+    1e-10 on every parameter."""
     from gadfit_b200 import LMsolver, workloads as W
     w = W.c4(iteration_limit=4)
     s = LMsolver(w.model)
     w.setup(s)
     s.fit(w.lambda0)
     _consistency_checks(s, 4)
-    # recovered shared parameters are close to the truth the data were made from
-    np.testing.assert_allclose([s.getParValue(k) for k in w.shared],
-                               [w.truth[0, k] for k in w.shared], rtol=2e-3)
+    assert s.timings()["omega"][1] >= 4  # the omega sweep ran in every iteration
 
 
 def test_full_size_c5_double_integral_block_arrow(c1):
