@@ -85,11 +85,12 @@ CUDA_ERROR = 10
 NCCL_ERROR = 11
 INVALID_ARGUMENT = 12
 NOT_AVAILABLE = 13
+TOO_MANY_PARAMETERS = 14
 
 # gadfit_b200_array
 JACOBIAN, JTJ, DTD, LEFT_SIDE, RIGHT_SIDE, RESIDUALS, INV_JTJ, DELTA1, DELTA2, OMEGA = range(10)
 
-# every symbol include/gadfit_b200.h declares (checked by tests/test_capi_symbols.py)
+# every symbol include/gadfit_b200.h declares (checked by tests/test_capi_host.py)
 CORE_SYMBOLS = [
     "create", "destroy", "add_dataset", "set_par", "default_settings",
     "set_settings", "fit", "get_par", "get_value", "chi2", "dof", "get_array",
@@ -98,7 +99,7 @@ CORE_SYMBOLS = [
 PRODUCT_ONLY_SYMBOLS = [
     "default_gadf_options", "set_gadf_options", "get_stop_reason", "set_log",
     "n_models", "model_info", "load_models", "n_launches", "jacobian_kernel_time",
-    "status_name", "set_device", "upload", "comm_unique_id", "set_comm",
+    "status_name", "set_device", "upload", "invalidate_data", "comm_unique_id", "set_comm",
     "partition", "measure_fp64_peak", "microbench", "comm_stats",
 ]
 
@@ -157,6 +158,7 @@ class Api:
                 "status_name": ([C.c_int], C.c_char_p),
                 "set_device": ([vp, C.c_int], C.c_int),
                 "upload": ([vp], C.c_int),
+                "invalidate_data": ([vp], C.c_int),
                 "comm_unique_id": ([vp], C.c_int),
                 "set_comm": ([vp, C.c_int, C.c_int, vp], C.c_int),
                 "partition": ([C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),

@@ -40,8 +40,13 @@ struct LmState
     int decision;   // 0 accept, 1 retry, 2 give up (gadfit_b200_trial)
     int i_lambda;   // consecutive rejections in this iteration
     int use_delta2; // acceleration passed the ratio test
-    int pad;
+    // Status bits raised by kernels during the fit (never cleared by them):
+    // bit 0 (fit_function.h k_status_workspace): an adaptive integrator ran
+    // out of panels; bit 1: a peer-memory collective timed out
+    unsigned flags;
 };
+constexpr unsigned kFlagWorkspace { 1U };
+constexpr unsigned kFlagPeerTimeout { 2U };
 
 // Per-data-set factorisation kept between the Schur step and the
 // back-substitution of the same trial

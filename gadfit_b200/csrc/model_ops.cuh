@@ -5,6 +5,8 @@
 #include "block_arrow_kernels.cuh"
 #include "device_util.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <memory>
 
 namespace gadfit_b200 {
@@ -102,8 +104,12 @@ struct ModelOpsImpl final : ModelOps
 {
     static constexpr int NP { Model::n_pars };
     using Shape = JacobianShape<Model>;
+    using WsShape = JacobianWsShape<Model>;
     int occupancy[3] { 1, 1, 1 };
     bool device_ready { false };
+    // GADFIT_B200_JAC=legacy: the round-1 Jacobian sweep (every warp both
+    // evaluates and contracts), kept for A/B measurements
+    bool legacy_jacobian { false };
 
     auto init_device() -> void override
     {
@@ -127,10 +133,30 @@ struct ModelOpsImpl final : ModelOps
         configure(k_jacobian<Model, false, true>);
         configure(k_jacobian<Model, true, false>);
         configure(k_jacobian<Model, true, true>);
+        const auto configure_ws { [](auto* kernel) {
+            GADFIT_CUDA_TRY(cudaFuncSetAttribute(kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(WsShape::smem_bytes)));
+            GADFIT_CUDA_TRY(cudaFuncSetAttribute(kernel,
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared));
+        } };
+        configure_ws(k_jacobian_ws<Model, false, false>);
+        configure_ws(k_jacobian_ws<Model, false, true>);
+        configure_ws(k_jacobian_ws<Model, true, false>);
+        configure_ws(k_jacobian_ws<Model, true, true>);
+        const char* jac { std::getenv("GADFIT_B200_JAC") };
+        legacy_jacobian = jac != nullptr && std::strcmp(jac, "legacy") == 0;
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model>, kThreads, 0));
-        GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &occupancy[1], k_jacobian<Model, true, false>, kThreads, Shape::smem_bytes));
+        if (legacy_jacobian) {
+            GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+              &occupancy[1], k_jacobian<Model, true, false>, kThreads, Shape::smem_bytes));
+        } else {
+            GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+              &occupancy[1], k_jacobian_ws<Model, true, false>, kJacThreads,
+              WsShape::smem_bytes));
+        }
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[2], k_omega<Model>, kThreads, 0));
         for (int& o : occupancy) {
@@ -167,6 +193,20 @@ struct ModelOpsImpl final : ModelOps
     {
         const bool store { J_out != nullptr || r_out != nullptr };
         const bool linear { loss == GADFIT_B200_LOSS_LINEAR };
+        if (!legacy_jacobian) {
+            const auto launch { [&](auto* kernel) {
+                kernel<<<grid, kJacThreads, WsShape::smem_bytes, st>>>(
+                  a, loss, slot_base, partials, J_out, r_out, n_points);
+            } };
+            if (store) {
+                linear ? launch(k_jacobian_ws<Model, true, true>)
+                       : launch(k_jacobian_ws<Model, true, false>);
+            } else {
+                linear ? launch(k_jacobian_ws<Model, false, true>)
+                       : launch(k_jacobian_ws<Model, false, false>);
+            }
+            return;
+        }
         const auto launch { [&](auto* kernel) {
             kernel<<<grid, kThreads, Shape::smem_bytes, st>>>(
               a, loss, slot_base, partials, J_out, r_out, n_points);

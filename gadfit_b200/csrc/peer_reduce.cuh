@@ -39,7 +39,20 @@ struct PeerTable
     PeerMailbox* box[kPeerMaxRanks]; // box[q]: mailbox in rank q's HBM
     int rank;
     int world;
+    // A rank that never joins the collective (it failed before launching its
+    // side) must not leave the others spinning for ever: after timeout_ns the
+    // wait gives up and raises kFlagPeerTimeout in *status (LmState::flags),
+    // which fit() reports as GADFIT_B200_NCCL_ERROR
+    unsigned long long timeout_ns;
+    unsigned* status;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, const unsigned long long v)
 {
@@ -77,7 +90,14 @@ peer_all_reduce_block(const PeerTable& t, double* __restrict__ buf, const int n,
     // 3. wait until every rank's contribution has landed in MY mailbox
     if (tid < t.world) {
         const unsigned long long* flag { &t.box[t.rank]->flags[parity][tid] };
+        const unsigned long long begin { global_timer_ns() };
         while (ld_acquire_sys(flag) < seq) {
+            if (global_timer_ns() - begin > t.timeout_ns) {
+                if (t.status != nullptr) {
+                    atomicOr(t.status, kFlagPeerTimeout);
+                }
+                break;
+            }
         }
     }
     __syncthreads();
@@ -207,6 +227,10 @@ struct PeerReduce
         }
         table.rank = rank;
         table.world = world;
+        // GADFIT_B200_PEER_TIMEOUT_S: seconds a rank waits for its peers (default 30)
+        const char* timeout_env { std::getenv("GADFIT_B200_PEER_TIMEOUT_S") };
+        const double timeout_s { timeout_env != nullptr ? std::atof(timeout_env) : 30.0 };
+        table.timeout_ns = static_cast<unsigned long long>((timeout_s > 0.0 ? timeout_s : 30.0) * 1e9);
         for (int q = 0; q < world && all_ok; ++q) {
             if (q == rank) {
                 table.box[q] = local;

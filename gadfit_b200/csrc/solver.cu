@@ -91,6 +91,15 @@ __global__ void k_fill(double* p, const long long n, const double v)
     }
 }
 
+// sigma -> 1 / sigma, once at upload: the sweeps multiply
+__global__ void k_invert(double* p, const long long n)
+{
+    const long long i { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
+    if (i < n) {
+        p[i] = 1.0 / p[i];
+    }
+}
+
 __global__ void k_copy_chi2_to_old(LmState* state)
 {
     state->old_chi2 = state->new_chi2;
@@ -202,7 +211,7 @@ struct SolverImpl
     std::vector<long long> local_begin; // first owned point of each local set
     std::vector<long long> local_count; // owned points of each local set
 
-    DeviceBuffer<double> d_x, d_y, d_sig;
+    DeviceBuffer<double> d_x, d_y, d_sig; // d_sig holds 1 / sigma
     DeviceBuffer<int> d_set_tile_begin;        // [n_local_sets + 1]
     DeviceBuffer<long long> d_set_point_begin; // [n_local_sets + 1]
     std::vector<int> h_tile_set;               // data set of each tile (host, for the slots)
@@ -409,7 +418,7 @@ struct SolverImpl
         GADFIT_CUDA_TRY(cudaMallocHost(&h_mirror, 2 * sizeof(LmState)));
         GADFIT_CUDA_TRY(cudaMallocHost(&h_scalar, 24 * sizeof(double)));
         ops->init_device();
-        d_state.ensure(3);
+        d_state.zero(3, stream);
         d_scratch.ensure(8);
         device_ready = true;
     }
@@ -550,6 +559,10 @@ struct SolverImpl
         copy_field(0, d_x.ptr);
         copy_field(1, d_y.ptr);
         copy_field(2, d_sig.ptr);
+        if (n_local_points > 0) {
+            k_invert<<<blocks_for(n_local_points, 256), 256, 0, stream>>>(d_sig.ptr, n_local_points);
+            launched();
+        }
 
         // Tiles
         h_tile_set.clear();
@@ -632,7 +645,7 @@ struct SolverImpl
     [[nodiscard]] auto sweep_args() const -> SweepArgs
     {
         return { d_x.ptr, d_y.ptr,      d_sig.ptr, d_set_tile_begin.ptr, d_set_point_begin.ptr,
-                 n_local_sets, n_tiles, d_par.ptr };
+                 n_local_sets, n_tiles, d_par.ptr, &d_state.ptr->flags };
     }
 
     // --------------------------------------------------------------- phases
@@ -751,6 +764,11 @@ struct SolverImpl
             launched();
         }
         if (part.split) {
+            if (n_tiles == 0) {
+                // a rank without points (every data set shorter than the number
+                // of ranks) contributes zeros, not last iteration's global sums
+                d_M.zero(static_cast<size_t>(std::max(n_local_sets, 1)) * NT, stream);
+            }
             all_reduce(d_M.ptr, static_cast<size_t>(n_local_sets) * NT);
         }
         t_jacobian.stop(stream);
@@ -860,6 +878,9 @@ struct SolverImpl
                 launched();
             }
             if (part.split) {
+                if (n_tiles == 0) {
+                    d_vsets.zero(static_cast<size_t>(std::max(n_local_sets, 1)) * NP, stream);
+                }
                 all_reduce(d_vsets.ptr, static_cast<size_t>(n_local_sets) * NP);
             }
             t_omega.stop(stream);
@@ -1222,6 +1243,39 @@ struct SolverImpl
         log_line("");
     }
 
+    // Status bits the kernels raised (LmState::flags) -> the status the
+    // reference reports by exception (numerical_integration.cpp:304,525:
+    // InsufficientIntegrationWorkspace) / a collective that timed out
+    auto throw_if_flagged(const unsigned flags) -> void
+    {
+        if ((flags & kFlagPeerTimeout) != 0U) {
+            throw StatusError { GADFIT_B200_NCCL_ERROR,
+                                "a peer-memory all-reduce timed out: another rank did not "
+                                "take part in the collective" };
+        }
+        if ((flags & kFlagWorkspace) != 0U) {
+            throw StatusError {
+                GADFIT_B200_INSUFFICIENT_INTEGRATION_WORKSPACE,
+                "an adaptive integral needed more than " + std::to_string(k_max_panels)
+                  + " panels (1-D) / " + std::to_string(k_max_panels_2d)
+                  + " rectangles (2-D) at some data point: loosen rel_error / abs_error of "
+                    "integrate() or narrow the range"
+            };
+        }
+    }
+    // Reads the live flags (one 48-byte copy + sync) and clears them
+    auto check_device_flags() -> void
+    {
+        GADFIT_CUDA_TRY(cudaMemcpyAsync(
+          h_mirror, d_state.ptr, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        const unsigned flags { h_mirror[0].flags };
+        if (flags != 0U) {
+            GADFIT_CUDA_TRY(cudaMemsetAsync(&d_state.ptr->flags, 0, sizeof(unsigned), stream));
+            throw_if_flagged(flags);
+        }
+    }
+
     // LMsolver::fit, lm_solver.cpp:401-511
     auto fit(const double lambda0) -> void
     {
@@ -1264,6 +1318,7 @@ struct SolverImpl
         launched();
         int i_iteration { 0 };
         bool finished { settings.iteration_limit == 0 };
+        bool finite_start { true };
         while (!finished) {
             ++i_iteration;
             if (small) {
@@ -1305,6 +1360,15 @@ struct SolverImpl
                   { rec.lambda, rec.new_chi2, rec.old_chi2, i_iteration, rec.decision });
                 lambda = now.lambda;
                 last_old_chi2 = now.old_chi2;
+                if (now.flags != 0U) {
+                    // as the reference's exception: the fit ends here; what has
+                    // been accepted so far stays in the solver
+                    t_main.stop(stream);
+                    n_iterations = std::max(i_iteration - 1, 0);
+                    download_parameters();
+                    fitted = true;
+                    throw_if_flagged(now.flags);
+                }
                 const bool chatty { !io_test(io_hide_all) && !io_test(io_final_only) };
                 if (rec.decision == 0) {
                     if (chatty) { // lm_solver.cpp:465-467
@@ -1323,7 +1387,12 @@ struct SolverImpl
                     }
                     --i_iteration;
                     finished = true;
-                    stop_reason = GADFIT_B200_STOP_LAMBDA_INCS;
+                    // NaN/inf at the start: every step is rejected (new < old is
+                    // false, as in the reference) -- tell it apart from a
+                    // converged fit
+                    finite_start = finite_start && std::isfinite(rec.old_chi2);
+                    stop_reason = finite_start ? GADFIT_B200_STOP_LAMBDA_INCS
+                                               : GADFIT_B200_STOP_NON_FINITE_CHI2;
                 }
             }
             if (i_iteration == settings.iteration_limit) {
@@ -1336,6 +1405,9 @@ struct SolverImpl
         t_main.stop(stream);
         n_iterations = i_iteration;
         download_parameters();
+        if (settings.iteration_limit == 0) {
+            check_device_flags(); // the initial chi2 sweep is all that ran
+        }
         for (PhaseTimer* t :
              { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
             t->collect();
@@ -1462,6 +1534,9 @@ struct SolverImpl
                                             stream));
             GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
             std::copy(h_gadf, h_gadf + kGadfSums + 1, sums);
+            if (!std::isfinite(sums[kGadfSums])) {
+                check_device_flags(); // a poisoned integral, not an ordinary bad step?
+            }
         } };
 
         const double umnigh_m { std::exp(-0.2) }; // :516
@@ -1593,6 +1668,7 @@ struct SolverImpl
         t_main.stop(stream);
         n_iterations = iterations;
         download_parameters();
+        check_device_flags();
         for (PhaseTimer* t :
              { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
             t->collect();
@@ -1611,6 +1687,9 @@ struct SolverImpl
         GADFIT_CUDA_TRY(cudaMemcpyAsync(
           h_scalar, d_scratch.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream));
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (!std::isfinite(h_scalar[0])) {
+            check_device_flags();
+        }
         return h_scalar[0];
     }
 
@@ -1882,6 +1961,13 @@ namespace gadfit_b200 {
 
 namespace {
 
+inline auto require_output(const void* p) -> void
+{
+    if (p == nullptr) {
+        throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "null output pointer" };
+    }
+}
+
 template <class F>
 auto guarded(gadfit_b200_solver* h, F&& f) -> int
 {
@@ -1958,7 +2044,9 @@ auto load_models(const char* path) -> int
     for (int i = 0; i < count(); ++i) {
         const char* name { nullptr };
         int n_pars { 0 };
-        if (info(i, &name, &n_pars) != 0 || name == nullptr || n_pars < 1 || n_pars > kMaxShared) {
+        // (functions with more than kMaxShared parameters are listed, so that
+        // create() can say why it refuses them)
+        if (info(i, &name, &n_pars) != 0 || name == nullptr || n_pars < 1) {
             dlclose(lib);
             return GADFIT_B200_INVALID_ARGUMENT;
         }
@@ -2030,6 +2118,9 @@ int gadfit_b200_create(const char* model_name, gadfit_b200_solver** out)
             const std::lock_guard lock { reg.mutex };
             for (const auto& m : reg.table) {
                 if (m.make_indexed != nullptr && std::string_view { m.name } == model_name) {
+                    if (m.n_pars > kMaxShared) {
+                        return GADFIT_B200_TOO_MANY_PARAMETERS;
+                    }
                     ops.reset(static_cast<ModelOps*>(m.make_indexed(m.plugin_index)));
                     break;
                 }
@@ -2166,23 +2257,33 @@ int gadfit_b200_get_par(gadfit_b200_solver* solver, int i_par, int i_dataset, do
             || i_dataset >= static_cast<int>(solver->sets.size())) {
             throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "index out of range" };
         }
+        require_output(out);
         *out = solver->par[static_cast<size_t>(i_dataset) * solver->NP + i_par];
     });
 }
 
 int gadfit_b200_get_value(gadfit_b200_solver* solver, double arg, int i_dataset, double* out)
 {
-    return guarded(solver, [&] { *out = solver->public_value(arg, i_dataset); });
+    return guarded(solver, [&] {
+        require_output(out);
+        *out = solver->public_value(arg, i_dataset);
+    });
 }
 
 int gadfit_b200_chi2(gadfit_b200_solver* solver, double* out)
 {
-    return guarded(solver, [&] { *out = solver->public_chi2(); });
+    return guarded(solver, [&] {
+        require_output(out);
+        *out = solver->public_chi2();
+    });
 }
 
 int gadfit_b200_dof(gadfit_b200_solver* solver, int* out)
 {
-    return guarded(solver, [&] { *out = solver->dof; });
+    return guarded(solver, [&] {
+        require_output(out);
+        *out = solver->dof;
+    });
 }
 
 int gadfit_b200_get_array(gadfit_b200_solver* solver,
@@ -2221,12 +2322,16 @@ int gadfit_b200_get_trace(gadfit_b200_solver* solver,
 
 int gadfit_b200_n_iterations(gadfit_b200_solver* solver, int* out)
 {
-    return guarded(solver, [&] { *out = solver->n_iterations; });
+    return guarded(solver, [&] {
+        require_output(out);
+        *out = solver->n_iterations;
+    });
 }
 
 int gadfit_b200_get_timings(gadfit_b200_solver* solver, gadfit_b200_timings* out)
 {
     return guarded(solver, [&] {
+        require_output(out);
         const PhaseTimer* timers[5] { &solver->t_jacobian,
                                       &solver->t_chi2,
                                       &solver->t_linalg,
@@ -2241,7 +2346,10 @@ int gadfit_b200_get_timings(gadfit_b200_solver* solver, gadfit_b200_timings* out
 
 int gadfit_b200_n_launches(gadfit_b200_solver* solver, long long* out)
 {
-    return guarded(solver, [&] { *out = solver->n_launches; });
+    return guarded(solver, [&] {
+        require_output(out);
+        *out = solver->n_launches;
+    });
 }
 
 int gadfit_b200_comm_stats(gadfit_b200_solver* solver,
@@ -2250,6 +2358,9 @@ int gadfit_b200_comm_stats(gadfit_b200_solver* solver,
                            long long* n_nccl_reductions)
 {
     return guarded(solver, [&] {
+        require_output(peer_reduce_active);
+        require_output(n_peer_reductions);
+        require_output(n_nccl_reductions);
         *peer_reduce_active = solver->peer.active ? 1 : 0;
         *n_peer_reductions = solver->n_peer_reductions;
         *n_nccl_reductions = solver->n_nccl_reductions;
@@ -2261,6 +2372,8 @@ int gadfit_b200_jacobian_kernel_time(gadfit_b200_solver* solver,
                                      int* launches)
 {
     return guarded(solver, [&] {
+        require_output(seconds_per_launch);
+        require_output(launches);
         // (fused small-problem path: the Jacobian phase is exactly the kernel)
         const auto& t { solver->t_jac_kernel.calls > 0 ? solver->t_jac_kernel
                                                         : solver->t_jacobian };
@@ -2289,8 +2402,9 @@ const char* gadfit_b200_status_name(int status)
                                  "CudaError",
                                  "NcclError",
                                  "InvalidArgument",
-                                 "NotAvailable" };
-    if (status < 0 || status > GADFIT_B200_NOT_AVAILABLE) {
+                                 "NotAvailable",
+                                 "TooManyParameters" };
+    if (status < 0 || status > GADFIT_B200_TOO_MANY_PARAMETERS) {
         return "?";
     }
     return names[status];
@@ -2316,8 +2430,16 @@ int gadfit_b200_upload(gadfit_b200_solver* solver)
     });
 }
 
+int gadfit_b200_invalidate_data(gadfit_b200_solver* solver)
+{
+    return guarded(solver, [&] { solver->data_uploaded = false; });
+}
+
 int gadfit_b200_comm_unique_id(void* id_128_bytes)
 {
+    if (id_128_bytes == nullptr) {
+        return GADFIT_B200_INVALID_ARGUMENT;
+    }
     try {
         auto& nccl { Nccl::instance() };
         ncclUniqueId id {};
@@ -2352,6 +2474,7 @@ int gadfit_b200_set_comm(gadfit_b200_solver* solver,
             nccl.check(nccl.commInitRank(&solver->comm, world_size, id, rank),
                        "ncclCommInitRank");
             solver->peer.setup(rank, world_size, solver->comm, solver->stream);
+            solver->peer.table.status = &solver->d_state.ptr->flags;
         }
         solver->rank = rank;
         solver->world = world_size;
@@ -2368,7 +2491,8 @@ int gadfit_b200_partition(int n_datasets,
                           int* split)
 {
     if (n_datasets < 0 || n_points == nullptr || world_size < 1 || rank < 0
-        || rank >= world_size) {
+        || rank >= world_size || first_dataset == nullptr || end_dataset == nullptr
+        || split == nullptr) {
         return GADFIT_B200_INVALID_ARGUMENT;
     }
     const Partition part { compute_partition(n_datasets, n_points, rank, world_size) };

@@ -59,7 +59,7 @@ struct SweepArgs
 {
     const double* __restrict__ x;
     const double* __restrict__ y;
-    const double* __restrict__ sig;
+    const double* __restrict__ inv_sig; // 1 / sigma (inverted once, at upload)
     // Tile geometry per DATA SET (not per tile): data set s owns the tiles
     // [set_tile_begin[s], set_tile_begin[s+1]) and the points
     // [set_point_begin[s], set_point_begin[s+1]) of the concatenated arrays
@@ -68,6 +68,9 @@ struct SweepArgs
     int n_sets;
     int n_tiles;
     const double* __restrict__ par; // [n_sets][NP] current parameters
+    // Status word of the sweep (LmState::flags): bit 0 = an adaptive
+    // integrator ran out of panels (fit_function.h, k_status_workspace)
+    unsigned* status;
 };
 
 // Walks the tiles of a CTA in ascending order.  Offsets and lengths are
@@ -195,14 +198,18 @@ __device__ __forceinline__ double loss_weight(const int loss_type, const double 
 //
 // sum_i ((y_i - f(x_i)) / sigma_i)^2 with passive parameters; the loss
 // function is NOT applied (lm_solver.cpp:521-524).  One partial per CTA.
+// `sig` holds 1 / sigma_i (inverted once, at upload: the division leaves the
+// sweeps).
 template <class Model>
 __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
   k_chi2(const SweepArgs a, double* __restrict__ block_partials)
 {
     constexpr int NP { Model::n_pars };
     constexpr int kChi2Unroll { Chi2Tuning<Model>::unroll };
+    using Pre = prepared_t<Model, ValueCtx>;
     __shared__ double s_par[NP];
     __shared__ double s_red[kThreads / 32];
+    __shared__ Pre s_prep; // prepare() of the current data set (empty without the hook)
     // Contiguous tile range of this CTA.  With kChi2Unroll > 1 the cut points
     // are moved up to the next multiple of kChi2Unroll tiles counted from the
     // start of the data set they fall into (or to its end): a range then never
@@ -241,8 +248,15 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
                 s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
             }
             __syncthreads();
+            if constexpr (HasPrepare<Model, ValueCtx>) {
+                if (tid == 0) {
+                    s_prep = prepare_of(Model {}, ValueCtx { s_par, a.status });
+                }
+                __syncthreads();
+            }
             cur_set = walk.set;
         }
+        const ValueCtx ctx { s_par, a.status };
         const long long base { walk.off(t) + tid };
         // W consecutive tiles of one data set (contiguous in memory; only the
         // last may be partial): the loads are issued together and the unrolled
@@ -257,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
             if constexpr (W == 1) {
                 // threads past the end of the data set evaluate nothing
                 if (tid < last_len) {
-                    const double f { value_of(Model {}(ValueCtx { s_par }, a.x[base])) };
-                    const double diff { (a.y[base] - f) / a.sig[base] };
+                    const double f { value_of(evaluate_prepared(Model {}, ctx, s_prep, a.x[base])) };
+                    const double diff { (a.y[base] - f) * a.inv_sig[base] };
                     sum += diff * diff;
                 }
                 ++t;
@@ -273,12 +287,12 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
                 const long long i { base + u * kTile };
                 x[u] = in ? a.x[i] : 0.0;
                 y[u] = in ? a.y[i] : 0.0;
-                sg[u] = in ? a.sig[i] : 1.0;
+                sg[u] = in ? a.inv_sig[i] : 1.0;
             }
 #pragma unroll
             for (int u = 0; u < W; ++u) {
-                const double f { value_of(Model {}(ValueCtx { s_par }, x[u])) };
-                const double diff { (y[u] - f) / sg[u] };
+                const double f { value_of(evaluate_prepared(Model {}, ctx, s_prep, x[u])) };
+                const double diff { (y[u] - f) * sg[u] };
                 if (u + 1 < W || tid < last_len) {
                     sum += diff * diff;
                 }
@@ -453,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
             const long long i { w.off(t) + tid };
             cp_async_8(&s_pre[buf][0][tid], a.x + i);
             cp_async_8(&s_pre[buf][1][tid], a.y + i);
-            cp_async_8(&s_pre[buf][2][tid], a.sig + i);
+            cp_async_8(&s_pre[buf][2][tid], a.inv_sig + i);
         }
         cp_async_commit();
     } };
@@ -480,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
         cp_async_wait_all();
         const double px { s_pre[buf][0][tid] };
         const double py { s_pre[buf][1][tid] };
-        const double psig { s_pre[buf][2][tid] };
+        const double inv_sig { s_pre[buf][2][tid] };
         if (t + 1 < t1) {
             TileWalker next { walk };
             next.advance_to(a, t + 1);
@@ -492,8 +506,7 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
         double* column { s_A + tid };
         if (tid < len) {
             const long long i { tile_off + tid };
-            const double inv_sig { 1.0 / psig };
-            const auto f { Model {}(GradCtx { s_par }, px) };
+            const auto f { evaluate(Model {}, GradCtx { s_par, a.status }, px) };
             // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
             const double res { (py - f.val) * inv_sig };
             // Linear loss (the default): the row scale 1/sigma is known before
@@ -549,6 +562,288 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
     }
 }
 
+// ------------------------------------------- Jacobian, warp-specialised
+//
+// k_jacobian above makes every warp alternate between evaluating its 32
+// points and contracting them, so all 256 threads hold the 2 * NBT accumulator
+// registers (24 of 80 for 21 columns) through the evaluation -- which then
+// spills -- and a warp's two phases can only overlap with OTHER warps' phases.
+// Here the two jobs belong to different warps of a 384-thread CTA:
+//
+//   warps 0-7   EVALUATION   one thread per point of the current tile:
+//               f, grad f (static-sparsity forward mode), augmented row into
+//               a double-buffered staging area [column][point]; no
+//               accumulators, the whole register budget serves the function.
+//   warps 8-11  CONTRACTION  warp m owns the rows of evaluation warps 2m and
+//               2m+1 (64 points = 16 k-steps of mma.sync.m8n8k4.f64 per tile)
+//               and keeps the accumulators of M_s for the whole run of tiles
+//               of a data set; the four warps are summed in fixed order when
+//               the data set changes.
+//
+// Hand-over through named barriers (bar.sync / bar.arrive, ids 1-4): FULL[b]
+// = evaluation warps arrive after writing stage b, contraction warps wait;
+// EMPTY[b] = the reverse.  The evaluation runs up to two tiles ahead.  The
+// (warp_id % 4) placement of warps on the SM's four sub-partitions gives each
+// sub-partition two evaluation warps and one contraction warp per CTA, two
+// CTAs per SM.
+//
+// Zero padding of the last 8-column block is never stored: lanes whose
+// fragment row lies beyond NA read from a shared all-zero line instead.
+constexpr int kJacEvalWarps { 8 };
+constexpr int kJacMmaWarps { 4 };
+constexpr int kJacThreads { (kJacEvalWarps + kJacMmaWarps) * 32 };
+static_assert(kJacEvalWarps * 32 == kTile);
+
+template <class Model>
+struct JacobianWsShape
+{
+    static constexpr int NP { Model::n_pars };
+    static constexpr int NA { NP + 1 };
+    static constexpr int NT { NA * (NA + 1) / 2 };
+    static constexpr int NB { (NA + 7) / 8 };
+    static constexpr int NBT { NB * (NB + 1) / 2 };
+    static constexpr int LDP { kTile + 4 };
+    using Pre = prepared_t<Model, GradCtx>;
+    // dynamic shared memory, in doubles
+    static constexpr size_t stage { static_cast<size_t>(NA) * LDP };   // x 2
+    static constexpr size_t zero_line { LDP };
+    static constexpr size_t flush { static_cast<size_t>(kJacMmaWarps) * NBT * 64 };
+    static constexpr size_t prefetch { 2 * 3 * kTile };
+    static constexpr size_t par { (NP + 1) & ~size_t { 1 } };
+    static constexpr size_t prep { (sizeof(Pre) + 7) / 8 };
+    static constexpr size_t smem_bytes {
+        sizeof(double) * (2 * stage + zero_line + flush + prefetch + par + prep)
+    };
+};
+
+__device__ __forceinline__ void named_bar_sync(const int id, const int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(const int id, const int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <class Model, bool kStore, bool kLinearLoss>
+__global__ void __launch_bounds__(kJacThreads, 2)
+  k_jacobian_ws(const SweepArgs a,
+                const int loss_type,
+                const int* __restrict__ slot_base,
+                double* __restrict__ partials,
+                double* __restrict__ J_out,
+                double* __restrict__ r_out,
+                const long long n_points)
+{
+    using Shape = JacobianWsShape<Model>;
+    using Pre = typename Shape::Pre;
+    constexpr int NP { Shape::NP };
+    constexpr int NA { Shape::NA };
+    constexpr int NT { Shape::NT };
+    constexpr int NB { Shape::NB };
+    constexpr int NBT { Shape::NBT };
+    constexpr int LDP { Shape::LDP };
+    constexpr int kBarFull { 1 };  // + buffer
+    constexpr int kBarEmpty { 3 }; // + buffer
+    constexpr int kBarEval { 5 };
+    constexpr int kBarMma { 6 };
+    extern __shared__ double s_dyn[];
+    double* const s_stage { s_dyn };                              // [2][NA][LDP]
+    double* const s_zero { s_stage + 2 * Shape::stage };          // [LDP]
+    double* const s_flush { s_zero + Shape::zero_line };          // [4][NBT][64]
+    double* const s_pre { s_flush + Shape::flush };               // [2][3][kTile]
+    double* const s_par { s_pre + Shape::prefetch };              // [NP]
+    Pre* const s_prep { reinterpret_cast<Pre*>(s_par + Shape::par) };
+
+    const int tid { static_cast<int>(threadIdx.x) };
+    const int warp { tid >> 5 };
+    for (int i = tid; i < LDP; i += kJacThreads) {
+        s_zero[i] = 0.0;
+    }
+    __syncthreads();
+
+    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
+                                    / gridDim.x) };
+    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
+                                    * (blockIdx.x + 1) / gridDim.x) };
+    if (t0 >= t1) {
+        return;
+    }
+    TileWalker walk {};
+    walk.seek(a, t0);
+    int cur_set { -1 };
+
+    if (warp < kJacEvalWarps) {
+        // ------------------------------------------------------ evaluation
+        const auto prefetch { [&](const TileWalker& w, const int t, const int buf) {
+            if (tid < w.len(t)) {
+                const long long i { w.off(t) + tid };
+                double* dst { s_pre + buf * 3 * kTile + tid };
+                cp_async_8(dst, a.x + i);
+                cp_async_8(dst + kTile, a.y + i);
+                cp_async_8(dst + 2 * kTile, a.inv_sig + i);
+            }
+            cp_async_commit();
+        } };
+        prefetch(walk, t0, 0);
+        for (int t = t0; t < t1; ++t) {
+            const int buf { (t - t0) & 1 };
+            walk.advance_to(a, t);
+            if (walk.set != cur_set) {
+                named_bar_sync(kBarEval, kTile); // everyone is done with the old parameters
+                if (tid < NP) {
+                    s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
+                }
+                named_bar_sync(kBarEval, kTile);
+                if constexpr (HasPrepare<Model, GradCtx>) {
+                    if (tid == 0) {
+                        *s_prep = prepare_of(Model {}, GradCtx { s_par, a.status });
+                    }
+                    named_bar_sync(kBarEval, kTile);
+                }
+                cur_set = walk.set;
+            }
+            const int len { walk.len(t) };
+            const long long tile_off { walk.off(t) };
+            cp_async_wait_all();
+            const double px { s_pre[buf * 3 * kTile + tid] };
+            const double py { s_pre[buf * 3 * kTile + kTile + tid] };
+            const double inv_sig { s_pre[buf * 3 * kTile + 2 * kTile + tid] };
+            if (t + 1 < t1) {
+                TileWalker next { walk };
+                next.advance_to(a, t + 1);
+                prefetch(next, t + 1, buf ^ 1);
+            }
+            if (t - t0 >= 2) {
+                named_bar_sync(kBarEmpty + buf, kJacThreads); // stage `buf` has been contracted
+            }
+            double* column { s_stage + buf * Shape::stage + tid };
+            if (tid < len) {
+                const long long i { tile_off + tid };
+                const auto f { evaluate_prepared(
+                  Model {}, GradCtx { s_par, a.status }, *s_prep, px) };
+                // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
+                const double res { (py - f.val) * inv_sig };
+                const double w { kLinearLoss ? 1.0 : loss_weight(loss_type, res) };
+                const double scale { kLinearLoss ? inv_sig : w * inv_sig };
+                double g[NP];
+                dense_gradient<NP>(f, g);
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const double jk { g[k] * scale };
+                    column[k * LDP] = jk;
+                    if constexpr (kStore) {
+                        if (J_out != nullptr) {
+                            J_out[static_cast<long long>(k) * n_points + i] = jk;
+                        }
+                    }
+                }
+                column[NP * LDP] = w * res;
+                if constexpr (kStore) {
+                    if (r_out != nullptr) {
+                        r_out[i] = w * res;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NA; ++k) {
+                    column[k * LDP] = 0.0;
+                }
+            }
+            named_bar_arrive(kBarFull + buf, kJacThreads);
+        }
+    } else {
+        // ----------------------------------------------------- contraction
+        const int lane { tid & 31 };
+        const int m { warp - kJacEvalWarps }; // rows [64 m, 64 m + 64) of every tile
+        const int mtid { tid - kJacEvalWarps * 32 };
+        const int frag_row { lane >> 2 }; // column within a block of 8
+        const int frag_pt { lane & 3 };   // point within a k-step of 4
+        // fragment source of each column block within a stage: the column's
+        // line, or the all-zero line for the padding of the last block
+        int frag_off[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int col { 8 * b + frag_row };
+            frag_off[b] = (col < NA ? col * LDP : static_cast<int>(s_zero - s_stage)) + 64 * m
+                          + frag_pt;
+        }
+        double acc[NBT][2];
+#pragma unroll
+        for (int b = 0; b < NBT; ++b) {
+            acc[b][0] = 0.0;
+            acc[b][1] = 0.0;
+        }
+        int slot { slot_base[blockIdx.x] };
+        // Sum the contraction warps in fixed order, one partial (packed triangle)
+        const auto flush { [&]() {
+#pragma unroll
+            for (int b = 0; b < NBT; ++b) {
+                double* dst { s_flush + (m * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
+                dst[0] = acc[b][0];
+                dst[1] = acc[b][1];
+                acc[b][0] = 0.0;
+                acc[b][1] = 0.0;
+            }
+            named_bar_sync(kBarMma, kJacMmaWarps * 32);
+            for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
+                int i { 0 };
+                int rem { e };
+                while (rem >= NA - i) {
+                    rem -= NA - i;
+                    ++i;
+                }
+                const int j { i + rem };
+                const int blk { tri_index(NB, i >> 3, j >> 3) };
+                const int within { (i & 7) * 8 + (j & 7) };
+                double total { 0.0 };
+#pragma unroll
+                for (int w = 0; w < kJacMmaWarps; ++w) {
+                    total += s_flush[(w * NBT + blk) * 64 + within];
+                }
+                partials[static_cast<long long>(slot) * NT + e] = total;
+            }
+            named_bar_sync(kBarMma, kJacMmaWarps * 32);
+            ++slot;
+        } };
+        for (int t = t0; t < t1; ++t) {
+            const int buf { (t - t0) & 1 };
+            walk.advance_to(a, t);
+            if (walk.set != cur_set) {
+                if (cur_set >= 0) {
+                    flush();
+                }
+                cur_set = walk.set;
+            }
+            named_bar_sync(kBarFull + buf, kJacThreads);
+            const double* stage { s_stage + buf * Shape::stage };
+            // rows beyond the end of a partial tile are zero; whole 32-row
+            // halves beyond it are skipped
+            const int rows { walk.len(t) - 64 * m };
+            const int ksteps { rows >= 64 ? 16 : (rows > 32 ? 16 : (rows > 0 ? 8 : 0)) };
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) {
+                double frag[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    frag[b] = stage[frag_off[b] + ks * 4];
+                }
+#pragma unroll
+                for (int bi = 0; bi < NB; ++bi) {
+#pragma unroll
+                    for (int bj = bi; bj < NB; ++bj) {
+                        dmma_m8n8k4(acc[tri_index(NB, bi, bj)], frag[bi], frag[bj]);
+                    }
+                }
+            }
+            if (t + 2 < t1) {
+                named_bar_arrive(kBarEmpty + buf, kJacThreads);
+            }
+        }
+        flush();
+    }
+}
+
 // ------------------------------------------------------------------ omega
 //
 // omega_i = f.dd / sigma_i along delta1 (lm_solver.cpp:366-377; no loss
@@ -566,9 +861,11 @@ __global__ void __launch_bounds__(kThreads)
           double* __restrict__ omega_out)
 {
     constexpr int NP { Model::n_pars };
+    using Pre = prepared_t<Model, Dir2Ctx>;
     __shared__ double s_par[NP];
     __shared__ double s_seed[NP];
     __shared__ double s_red[kThreads / 32];
+    __shared__ Pre s_prep;
     const int tid { static_cast<int>(threadIdx.x) };
     const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
                                     / gridDim.x) };
@@ -608,12 +905,19 @@ __global__ void __launch_bounds__(kThreads)
                 s_seed[tid] = seed[static_cast<long long>(walk.set) * NP + tid];
             }
             __syncthreads();
+            if constexpr (HasPrepare<Model, Dir2Ctx>) {
+                if (tid == 0) {
+                    s_prep = prepare_of(Model {}, Dir2Ctx { s_par, s_seed, a.status });
+                }
+                __syncthreads();
+            }
             cur_set = walk.set;
         }
         if (tid < walk.len(t)) {
             const long long i { walk.off(t) + tid };
-            const Dir2 f { Model {}(Dir2Ctx { s_par, s_seed }, a.x[i]) };
-            const double omega { f.dd / a.sig[i] };
+            const Dir2 f { evaluate_prepared(
+              Model {}, Dir2Ctx { s_par, s_seed, a.status }, s_prep, a.x[i]) };
+            const double omega { f.dd * a.inv_sig[i] };
             if (omega_out != nullptr) {
                 omega_out[i] = omega;
             }
@@ -633,7 +937,7 @@ __global__ void __launch_bounds__(kThreads)
 template <class Model>
 __global__ void k_value(const double* __restrict__ par, const double arg, double* out)
 {
-    *out = value_of(Model {}(ValueCtx { par }, arg));
+    *out = value_of(evaluate(Model {}, ValueCtx { par }, arg));
 }
 
 } // namespace gadfit_b200

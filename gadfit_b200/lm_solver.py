@@ -79,6 +79,10 @@ class InvalidArgument(GADfitException):
     pass
 
 
+class TooManyParameters(GADfitException):
+    """more than 32 parameters in a fitting function"""
+
+
 class NotAvailable(GADfitException):
     pass
 
@@ -97,6 +101,7 @@ _STATUS_TO_EXCEPTION = {
     _capi.NCCL_ERROR: NcclError,
     _capi.INVALID_ARGUMENT: InvalidArgument,
     _capi.NOT_AVAILABLE: NotAvailable,
+    _capi.TOO_MANY_PARAMETERS: TooManyParameters,
 }
 
 
@@ -156,7 +161,7 @@ class GadfOptions:
 
 
 STOP_REASONS = ("iteration_limit", "lambda_incs", "chi2_abs", "chi2_rel", "grad_chi2", "cos_phi",
-                "rel_error", "rel_error_global")
+                "rel_error", "rel_error_global", "non_finite_chi2")
 
 
 def _as_f64(a) -> np.ndarray:
@@ -410,6 +415,12 @@ class LMsolver:
 
     def upload(self):
         self._check(self._api.upload(self._h))
+
+    def invalidateData(self):
+        """The data arrays were changed in place: copy them to HBM again at the
+        next fit() / chi2() / upload().  (The reference re-reads the caller's
+        arrays at every fit(), lm_solver.h:105-113.)"""
+        self._check(self._api.invalidate_data(self._h))
 
     def setComm(self, rank: int, world_size: int, unique_id: bytes):
         assert len(unique_id) == 128

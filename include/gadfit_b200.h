@@ -42,13 +42,21 @@ typedef enum gadfit_b200_status
     GADFIT_B200_NEGATIVE_DEGREES_OF_FREEDOM = 5, /* lm_solver.cpp:137-139 */
     GADFIT_B200_NO_FITTING_PARAMETERS = 6,    /* lm_solver.cpp:187-189 */
     GADFIT_B200_NO_GLOBAL_PARAMETERS = 7,     /* lm_solver.cpp:129-131 */
+    /* numerical_integration.cpp:304,525: an adaptive integrate() ran out of
+     * panels at some data point.  The device workspace is 96 panels (1-D) /
+     * 64 rectangles (2-D) per evaluation against the reference's default of
+     * 1000 (numerical_integration.h:40); fit() / chi2() return this status,
+     * the steps accepted before it stay in the solver. */
     GADFIT_B200_INSUFFICIENT_INTEGRATION_WORKSPACE = 8,
     /* conditions that have no reference counterpart */
     GADFIT_B200_UNKNOWN_MODEL = 9,
     GADFIT_B200_CUDA_ERROR = 10,
     GADFIT_B200_NCCL_ERROR = 11,
     GADFIT_B200_INVALID_ARGUMENT = 12,
-    GADFIT_B200_NOT_AVAILABLE = 13
+    GADFIT_B200_NOT_AVAILABLE = 13,
+    /* create(): the fitting function has more than 32 parameters (the
+     * parameter roles and the static-sparsity masks are 32-bit words) */
+    GADFIT_B200_TOO_MANY_PARAMETERS = 14
 } gadfit_b200_status;
 
 /* Loss functions, lm_solver.h:77-82 */
@@ -147,7 +155,12 @@ typedef enum gadfit_b200_stop_reason
     GADFIT_B200_STOP_GRAD_CHI2 = 4,       /* :845-857 */
     GADFIT_B200_STOP_COS_PHI = 5,         /* :858-881 */
     GADFIT_B200_STOP_REL_ERROR = 6,       /* :882-894 */
-    GADFIT_B200_STOP_REL_ERROR_GLOBAL = 7 /* :895-903 */
+    GADFIT_B200_STOP_REL_ERROR_GLOBAL = 7, /* :895-903 */
+    /* chi2 was NaN or infinite at the start: every trial step is rejected
+     * (new < old is false, lm_solver.cpp:462) and fit() gives up after
+     * lambda_incs + 1 trials exactly as the reference does -- but the caller
+     * can tell it apart from a converged fit */
+    GADFIT_B200_STOP_NON_FINITE_CHI2 = 8
 } gadfit_b200_stop_reason;
 
 /* The five phase timers of the reference (lm_solver.h:140-144, table printed
@@ -289,6 +302,11 @@ GADFIT_B200_API const char* gadfit_b200_status_name(int status);
 GADFIT_B200_API int gadfit_b200_set_device(gadfit_b200_solver* solver, int device);
 /* Copy the borrowed data sets to HBM now instead of at the first fit() */
 GADFIT_B200_API int gadfit_b200_upload(gadfit_b200_solver* solver);
+/* The reference reads the caller's arrays at every fit() (it holds spans,
+ * lm_solver.h:105-113); here they are copied to HBM once.  After changing
+ * x / y / errors in place, call this: the next fit() / chi2() / upload()
+ * copies them again (the arrays must then be alive again until it has). */
+GADFIT_B200_API int gadfit_b200_invalidate_data(gadfit_b200_solver* solver);
 
 /* One process per GPU.  Rank 0 obtains an id, the caller broadcasts the 128
  * bytes (torch.distributed / MPI / sockets) and every rank attaches.  All

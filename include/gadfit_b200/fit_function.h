@@ -16,8 +16,24 @@
 //   Dir2Ctx   par<K>(c) is Dir2 seeded with   -> omega sweep (lm_solver.cpp:362-380,
 //             d = delta1[column], dd = 0         fit_function.cpp:45-51)
 //
+// PREPARE HOOK (optional).  Sub-expressions that depend on the parameters only
+// -- 1/w, a table of exp(-k u_i^2) at the quadrature nodes -- need not be
+// recomputed for every data point: a function may add
+//
+//     template <class Ctx> GADFIT_HD auto prepare(const Ctx& c) const;   // any aggregate of AD values
+//     template <class Ctx, class Pre>
+//     GADFIT_HD auto operator()(const Ctx& c, const Pre& pre, double x) const;
+//
+// The sweeps call prepare() once per DATA SET (parameters are per data set)
+// and keep the result in shared memory; evaluate(model, ctx, x) below is the
+// one entry point and, for contexts without a cache (the reference's AdVar in
+// oracle/ref_harness.cpp, the oracle's dual), calls prepare() at every
+// evaluation -- the same arithmetic, so the source of a function stays single.
+//
 // c.kronrod(...) / c.kronrod2d(...) give the fixed 15-point Kronrod panel of
-// the reference (numerical_integration.cpp:133-148,189-215);
+// the reference (numerical_integration.cpp:133-148,189-215); the *_indexed
+// variants also hand the integrand the node indices, so that it can look up
+// what prepare() tabulated at the nodes (kronrod_node());
 // c.integrate(lower, upper, f(ctx, t), rel_error) its adaptive G7/K15 (or, as
 // c.template integrate<PTS>(...), the Fortran version's G10/K21 ... G30/K61)
 // integrator incl. AD-valued bounds (numerical_integration.cpp:242-423);
@@ -27,6 +43,8 @@
 
 #include "dual.h"
 #include "quadrature.h"
+
+#include <utility>
 
 namespace gadfit_b200 {
 
@@ -48,12 +66,37 @@ struct QuadratureMixin
         return gadfit_b200::kronrod2d(
           outer_lower, outer_upper, inner_lower, inner_upper, f);
     }
+    // f(t, i): i = index of the node t = kronrod_node(i, lower, upper)
+    template <class F>
+    GADFIT_HD auto kronrod_indexed(const double lower, const double upper, F&& f) const
+    {
+        return gadfit_b200::kronrod_indexed(lower, upper, f);
+    }
+    // f(u, v, i, j): u = inner node i, v = outer node j
+    template <class F>
+    GADFIT_HD auto kronrod2d_indexed(const double outer_lower,
+                                     const double outer_upper,
+                                     const double inner_lower,
+                                     const double inner_upper,
+                                     F&& f) const
+    {
+        return gadfit_b200::kronrod2d_indexed(
+          outer_lower, outer_upper, inner_lower, inner_upper, f);
+    }
 };
+
+// Bit 0 of the status word a context may carry: an adaptive integrator ran
+// out of panels (the reference throws InsufficientIntegrationWorkspace,
+// numerical_integration.cpp:304,525)
+constexpr unsigned k_status_workspace { 1U };
 
 struct ValueCtx : QuadratureMixin
 {
     const double* p;
-    GADFIT_HD explicit ValueCtx(const double* p) : p { p } {}
+    unsigned* status; // sweep-wide status word (device memory) or nullptr
+    GADFIT_HD explicit ValueCtx(const double* p, unsigned* status = nullptr)
+      : p { p }, status { status }
+    {}
     GADFIT_HD ValueCtx passive() const { return *this; }
     template <int PTS = 15, class BL, class BU, class F>
     GADFIT_HD auto integrate(const BL& lower,
@@ -85,8 +128,11 @@ struct ValueCtx : QuadratureMixin
 struct GradCtx : QuadratureMixin
 {
     const double* p;
-    GADFIT_HD explicit GradCtx(const double* p) : p { p } {}
-    GADFIT_HD ValueCtx passive() const { return ValueCtx { p }; }
+    unsigned* status;
+    GADFIT_HD explicit GradCtx(const double* p, unsigned* status = nullptr)
+      : p { p }, status { status }
+    {}
+    GADFIT_HD ValueCtx passive() const { return ValueCtx { p, status }; }
     template <int PTS = 15, class BL, class BU, class F>
     GADFIT_HD auto integrate(const BL& lower,
                              const BU& upper,
@@ -122,9 +168,11 @@ struct Dir2Ctx : QuadratureMixin
     const double* p;
     // Direction: delta1 of the column this parameter maps to, 0 if passive
     const double* seed;
-    GADFIT_HD Dir2Ctx(const double* p, const double* seed) : p { p }, seed { seed }
+    unsigned* status;
+    GADFIT_HD Dir2Ctx(const double* p, const double* seed, unsigned* status = nullptr)
+      : p { p }, seed { seed }, status { status }
     {}
-    GADFIT_HD ValueCtx passive() const { return ValueCtx { p }; }
+    GADFIT_HD ValueCtx passive() const { return ValueCtx { p, status }; }
     template <int PTS = 15, class BL, class BU, class F>
     GADFIT_HD auto integrate(const BL& lower,
                              const BU& upper,
@@ -157,6 +205,59 @@ template <int K, class Ctx>
 GADFIT_HD auto par(const Ctx& c)
 {
     return c.template get<K>();
+}
+
+// ---- prepare hook ----------------------------------------------------------
+template <class Model, class Ctx>
+concept HasPrepare = requires(const Model& m, const Ctx& c) { m.prepare(c); };
+
+struct NoPrepared
+{};
+
+template <class Model, class Ctx, bool = HasPrepare<Model, Ctx>>
+struct PreparedOf
+{
+    using type = NoPrepared;
+};
+template <class Model, class Ctx>
+struct PreparedOf<Model, Ctx, true>
+{
+    using type = decltype(std::declval<const Model&>().prepare(std::declval<const Ctx&>()));
+};
+template <class Model, class Ctx>
+using prepared_t = typename PreparedOf<Model, Ctx>::type;
+
+// What prepare() gives for this context (an empty struct without the hook)
+template <class Model, class Ctx>
+GADFIT_HD auto prepare_of(const Model& m, const Ctx& c) -> prepared_t<Model, Ctx>
+{
+    if constexpr (HasPrepare<Model, Ctx>) {
+        return m.prepare(c);
+    } else {
+        return {};
+    }
+}
+
+// f(x) given what prepare_of() returned for the same context
+template <class Model, class Ctx, class Pre>
+GADFIT_HD auto evaluate_prepared(const Model& m, const Ctx& c, const Pre& pre, const double x)
+{
+    if constexpr (HasPrepare<Model, Ctx>) {
+        return m(c, pre, x);
+    } else {
+        return m(c, x);
+    }
+}
+
+// f(x) from scratch: the entry point of contexts that keep no cache
+template <class Model, class Ctx>
+GADFIT_HD auto evaluate(const Model& m, const Ctx& c, const double x)
+{
+    if constexpr (HasPrepare<Model, Ctx>) {
+        return m(c, m.prepare(c), x);
+    } else {
+        return m(c, x);
+    }
 }
 
 // Semi-infinite integration ranges, as in the Fortran version

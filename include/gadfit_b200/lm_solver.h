@@ -183,7 +183,13 @@ public:
         // The reference logs its iteration results through spdlog by default
         // (lm_solver.cpp:465-467,587-654, pattern "%v" in its example): same
         // lines, to stdout, unless the caller installs another sink.
-        setLog(&LMsolver::printLine, nullptr);
+        try {
+            setLog(&LMsolver::printLine, nullptr);
+        } catch (...) {
+            gadfit_b200_destroy(handle); // no destructor runs for a throwing constructor
+            handle = nullptr;
+            throw;
+        }
     }
     // Where the text output of fit() goes (gadfit_b200_set_log); nullptr = nowhere
     auto setLog(gadfit_b200_log_fn sink, void* user) -> void
@@ -192,7 +198,9 @@ public:
     }
     LMsolver(const LMsolver&) = delete;
     auto operator=(const LMsolver&) -> LMsolver& = delete;
-    LMsolver(LMsolver&& other) noexcept : handle { other.handle }, settings { other.settings }
+    LMsolver(LMsolver&& other) noexcept
+      : handle { other.handle }, buffer { std::move(other.buffer) },
+        settings { std::move(other.settings) }
     {
         other.handle = nullptr;
     }
@@ -202,6 +210,14 @@ public:
             gadfit_b200_destroy(handle);
         }
     }
+
+    // The data arrays are BORROWED, as in the reference -- but the reference
+    // reads them at every fit() (it keeps spans, lm_solver.h:105-113), whereas
+    // here they are copied to HBM once, at the first fit() / chi2() or at
+    // upload().  After changing x / y / errors in place call invalidateData():
+    // the next fit() copies them again.
+    auto upload() -> void { check(gadfit_b200_upload(handle)); }
+    auto invalidateData() -> void { check(gadfit_b200_invalidate_data(handle)); }
 
     // lm_solver.h:158-167.  Arrays are borrowed, as in the reference.
     auto addDataset(const auto& x_data, const auto& y_data, const auto& errors) -> void

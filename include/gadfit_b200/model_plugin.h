@@ -59,7 +59,14 @@ struct Registrar
     Registrar()
     {
         registry().push_back({ Model::name, Model::n_pars, []() -> ModelOps* {
-                                  return new ModelOpsImpl<Model> {};
+                                  // more than 32 parameters: listed, but the kernels cannot
+                                  // be instantiated (32-bit role / sparsity masks);
+                                  // gadfit_b200_create answers GADFIT_B200_TOO_MANY_PARAMETERS
+                                  if constexpr (Model::n_pars <= kMaxShared) {
+                                      return new ModelOpsImpl<Model> {};
+                                  } else {
+                                      return nullptr;
+                                  }
                               } });
     }
 };

@@ -106,6 +106,50 @@ GADFIT_HD auto kronrod2d(const double outer_lower,
     return outer_scale * inner_scale * sum;
 }
 
+// Node i of the 15-point panel over [lower, upper], computed exactly as the
+// fixed rules (and the reference, numerical_integration.cpp:139-144) do: what
+// a fitting function's prepare() tabulates per node matches the node the
+// integrand is later called with.
+GADFIT_HD double kronrod_node(const int i, const double lower, const double upper)
+{
+    const double scale { (upper - lower) / 2 };
+    const double shift { (lower + upper) / 2 };
+    return scale * k15_root(i) + shift;
+}
+
+// The 2-D rule with the node indices handed to the integrand: f(u, v, i, j),
+// u = inner node i, v = outer node j (same nodes, weights and summation order
+// as kronrod2d above)
+template <class F>
+GADFIT_HD auto kronrod2d_indexed(const double outer_lower,
+                                 const double outer_upper,
+                                 const double inner_lower,
+                                 const double inner_upper,
+                                 F&& f)
+{
+    const double outer_scale { (outer_upper - outer_lower) / 2 };
+    const double outer_shift { (outer_lower + outer_upper) / 2 };
+    const double inner_scale { (inner_upper - inner_lower) / 2 };
+    const double inner_shift { (inner_lower + inner_upper) / 2 };
+    auto sum { (k15_weight(0) * k15_weight(0))
+               * f(Passive { inner_scale * k15_root(0) + inner_shift },
+                   Passive { outer_scale * k15_root(0) + outer_shift },
+                   0,
+                   0) };
+#pragma unroll 1
+    for (int i = 0; i < k15_size; ++i) {
+        const Passive u { inner_scale * k15_root(i) + inner_shift };
+        const double wi { k15_weight(i) };
+#pragma unroll 1
+        for (int j = (i == 0 ? 1 : 0); j < k15_size; ++j) {
+            sum = sum
+                  + (wi * k15_weight(j))
+                      * f(u, Passive { outer_scale * k15_root(j) + outer_shift }, i, j);
+        }
+    }
+    return outer_scale * inner_scale * sum;
+}
+
 
 // ===========================================================================
 // Adaptive Gauss-Kronrod (G7/K15) integration, 1-D
@@ -130,6 +174,22 @@ GADFIT_HD auto kronrod2d(const double outer_lower,
 // InsufficientIntegrationWorkspace.
 
 constexpr int k_max_panels { 96 };
+
+// Sets bit 0 of the context's status word, if it carries one (the device
+// contexts of fit_function.h do; host-side test contexts need not)
+template <class Ctx>
+GADFIT_HD void report_workspace_exhausted(const Ctx& c)
+{
+    if constexpr (requires { c.status; }) {
+        if (c.status != nullptr) {
+#if defined(__CUDA_ARCH__)
+            atomicOr(c.status, 1U);
+#else
+            *c.status |= 1U;
+#endif
+        }
+    }
+}
 constexpr double k_default_rel_error { 2.220446049250313e-14 }; // 1e2 * epsilon, numerical_integration.h:37-38
 
 #define GADFIT_G7_WEIGHTS                                                      \
@@ -212,6 +272,21 @@ GADFIT_HD auto kronrod(const double lower, const double upper, F&& f)
 #pragma unroll 1
     for (int i = 1; i < Rule::size; ++i) {
         sum = sum + Rule::weight(i) * f(Passive { scale * Rule::root(i) + shift });
+    }
+    return scale * sum;
+}
+
+// The same with the node index handed to the integrand: f(t, i)
+template <int PTS = 15, class F>
+GADFIT_HD auto kronrod_indexed(const double lower, const double upper, F&& f)
+{
+    using Rule = KronrodRule<PTS>;
+    const double scale { (upper - lower) / 2 };
+    const double shift { (lower + upper) / 2 };
+    auto sum { Rule::weight(0) * f(Passive { scale * Rule::root(0) + shift }, 0) };
+#pragma unroll 1
+    for (int i = 1; i < Rule::size; ++i) {
+        sum = sum + Rule::weight(i) * f(Passive { scale * Rule::root(i) + shift }, i);
     }
     return scale * sum;
 }
@@ -331,7 +406,11 @@ GADFIT_HD auto integrate(const Ctx& c,
         result = result + kronrod<PTS>(lo[i], hi[i], [&](const Passive& t) { return f(c, t); });
     }
     if (n_panels == 0) {
-        // workspace exhausted: poison the value (=> the step is rejected)
+        // workspace exhausted: the status word of the context is set -- fit()
+        // then returns GADFIT_B200_INSUFFICIENT_INTEGRATION_WORKSPACE, the
+        // counterpart of the reference's exception -- and the value is
+        // poisoned so that no step computed from it can be accepted
+        report_workspace_exhausted(c);
         result = result * (0.0 / 0.0);
     }
     return leibniz(c, f, leibniz(c, f, result, lower_bound, -1.0), upper_bound, 1.0);
@@ -516,7 +595,8 @@ GADFIT_HD auto integrate2d(const Ctx& c,
         result = result + kronrod2d(by1[i], by2[i], bx1[i], bx2[i], active);
     }
     if (n_panels == 0) {
-        result = result * (0.0 / 0.0); // workspace exhausted => rejected step
+        report_workspace_exhausted(c); // see integrate()
+        result = result * (0.0 / 0.0);
     }
     // traceRecordY1, Y2, X1, X2 in the reference's order (:1131-1144)
     auto r1 { leibniz2d<0>(c, f, result, y1_bound, x1_bound, x2_bound, -1.0, rel_error, abs_error) };

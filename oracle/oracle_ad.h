@@ -621,6 +621,25 @@ struct Ctx
     {
         return gadfit_oracle::kronrod2d(ol, ou, il, iu, f);
     }
+    // the integrand also receives the node indices (fit_function.h)
+    template <class F>
+    auto kronrod_indexed(const double lower, const double upper, F&& f) const -> FVar
+    {
+        int i { 0 };
+        return gadfit_oracle::kronrod(lower, upper, [&](const FVar& t) { return f(t, i++); });
+    }
+    template <class F>
+    auto kronrod2d_indexed(const double ol, const double ou, const double il, const double iu,
+                           F&& f) const -> FVar
+    {
+        int n { 0 }; // numerical_integration.cpp:204-212: inner node i outer loop, outer node j inner loop
+        return gadfit_oracle::kronrod2d(ol, ou, il, iu, [&](const FVar& u, const FVar& v) {
+            const int i { n / 15 };
+            const int j { n % 15 };
+            ++n;
+            return f(u, v, i, j);
+        });
+    }
 };
 
 } // namespace gadfit_oracle

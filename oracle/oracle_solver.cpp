@@ -981,7 +981,7 @@ int gadfit_oracle_create(const char* model_name, OracleSolver** out)
         if (std::strcmp(model_name, Model::name) == 0) {
             solver->NP = Model::n_pars;
             solver->body = [](const FVar* p, double x) {
-                return FVar { Model {}(gadfit_oracle::Ctx { p, Model::n_pars }, x) };
+                return FVar { gadfit_b200::evaluate(Model {}, gadfit_oracle::Ctx { p, Model::n_pars }, x) };
             };
         }
     } };

@@ -58,6 +58,32 @@ struct RefCtx
           lower,
           upper);
     }
+    // The integrand also receives the index of the node it is called at
+    // (include/gadfit_b200/fit_function.h): gadfit::kronrod visits its nodes in
+    // table order (numerical_integration.cpp:141-145, 204-212), so counting
+    // the calls gives the index.
+    template <class F>
+    auto kronrod_indexed(const double lower, const double upper, F&& f) const -> gadfit::AdVar
+    {
+        int i { 0 };
+        return kronrod(lower, upper, [&](const gadfit::AdVar& t) { return f(t, i++); });
+    }
+    template <class F>
+    auto kronrod2d_indexed(const double outer_lower,
+                           const double outer_upper,
+                           const double inner_lower,
+                           const double inner_upper,
+                           F&& f) const -> gadfit::AdVar
+    {
+        int n { 0 };
+        return kronrod2d(outer_lower, outer_upper, inner_lower, inner_upper,
+                         [&](const gadfit::AdVar& u, const gadfit::AdVar& v) {
+                             const int i { n / 15 };
+                             const int j { n % 15 };
+                             ++n;
+                             return f(u, v, i, j);
+                         });
+    }
     // gadfit::integrate, numerical_integration.h:83-113 (double or AdVar bounds)
     template <class BL, class BU, class F>
     auto integrate(const BL& lower,
@@ -124,7 +150,7 @@ template <class Model>
 auto makeSignature() -> gadfit::fitSignature
 {
     return [](const std::vector<gadfit::AdVar>& parameters, const double x) {
-        return gadfit::AdVar { Model {}(RefCtx { parameters }, x) };
+        return gadfit::AdVar { gadfit_b200::evaluate(Model {}, RefCtx { parameters }, x) };
     };
 }
 

@@ -19,7 +19,46 @@ __global__ void k_dual_check(double* out)
     }
 }
 
+// math_exp / math_rcp of dual.h beside CUDA's exp() and 1.0 / x
+__global__ void k_math_check(const double* x, const int n, double* out)
+{
+    const int i { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (i < n) {
+        out[i] = gadfit_b200::math_exp(x[i]);
+        out[n + i] = ::exp(x[i]);
+        out[2 * n + i] = gadfit_b200::math_rcp(x[i]);
+        out[3 * n + i] = 1.0 / x[i];
+    }
+}
+
 } // namespace
+
+// out[0..n) = math_exp(x), [n..2n) = CUDA exp(x), [2n..3n) = math_rcp(x),
+// [3n..4n) = 1.0 / x, all evaluated in a kernel
+extern "C" __attribute__((visibility("default"))) int device_math_check(const double* x,
+                                                                          int n,
+                                                                          double* out)
+{
+    double* d_x { nullptr };
+    double* d_out { nullptr };
+    cudaError_t err { cudaMalloc(&d_x, n * sizeof(double)) };
+    if (err == cudaSuccess) {
+        err = cudaMalloc(&d_out, 4 * n * sizeof(double));
+    }
+    if (err == cudaSuccess) {
+        err = cudaMemcpy(d_x, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (err == cudaSuccess) {
+        k_math_check<<<(n + 255) / 256, 256>>>(d_x, n, d_out);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        err = cudaMemcpy(out, d_out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_x);
+    cudaFree(d_out);
+    return static_cast<int>(err);
+}
 
 // Returns 0 on success, a negative number if `cap` is too small, a CUDA error
 // code otherwise; *n_entries / *width describe the layout of `out`.
