@@ -604,7 +604,8 @@ struct JacobianWsShape
     static constexpr int NBT { NB * (NB + 1) / 2 };
     static constexpr int LDP { kTile + 4 };
     using Pre = prepared_t<Model, GradCtx>;
-    // dynamic shared memory, in doubles
+    // dynamic shared memory, in doubles (config 2, 21 columns: 111.5 KiB, two
+    // CTAs per SM with their 1 KiB system reserve = 225 of 228 KiB)
     static constexpr size_t stage { static_cast<size_t>(NA) * LDP };   // x 2
     static constexpr size_t zero_line { LDP };
     static constexpr size_t flush { static_cast<size_t>(kJacMmaWarps) * NBT * 64 };
@@ -759,15 +760,10 @@ __global__ void __launch_bounds__(kJacThreads, 2)
         const int mtid { tid - kJacEvalWarps * 32 };
         const int frag_row { lane >> 2 }; // column within a block of 8
         const int frag_pt { lane & 3 };   // point within a k-step of 4
-        // fragment source of each column block within a stage: the column's
-        // line, or the all-zero line for the padding of the last block
-        int frag_off[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const int col { 8 * b + frag_row };
-            frag_off[b] = (col < NA ? col * LDP : static_cast<int>(s_zero - s_stage)) + 64 * m
-                          + frag_pt;
-        }
+        // fragment source of this lane within a column line; the lanes of the
+        // padding columns of the last block read the all-zero line instead
+        const int frag_in_line { 64 * m + frag_pt };
+        const bool last_is_padding { 8 * (NB - 1) + frag_row >= NA };
         double acc[NBT][2];
 #pragma unroll
         for (int b = 0; b < NBT; ++b) {
@@ -817,6 +813,14 @@ __global__ void __launch_bounds__(kJacThreads, 2)
             }
             named_bar_sync(kBarFull + buf, kJacThreads);
             const double* stage { s_stage + buf * Shape::stage };
+            const double* frag_src[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
+            }
+            if (last_is_padding) {
+                frag_src[NB - 1] = s_zero + frag_in_line;
+            }
             // rows beyond the end of a partial tile are zero; whole 32-row
             // halves beyond it are skipped
             const int rows { walk.len(t) - 64 * m };
@@ -826,7 +830,7 @@ __global__ void __launch_bounds__(kJacThreads, 2)
                 double frag[NB];
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    frag[b] = stage[frag_off[b] + ks * 4];
+                    frag[b] = frag_src[b][ks * 4];
                 }
 #pragma unroll
                 for (int bi = 0; bi < NB; ++bi) {

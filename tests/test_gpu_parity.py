@@ -13,6 +13,11 @@ from test_oracle import _check_kat, _run_exception_sections
 pytestmark = pytest.mark.gpu
 
 
+def _host_threads():
+    import os
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 @pytest.mark.parametrize("sc", scenarios.C1_SCENARIOS, ids=lambda s: s["name"])
 def test_reference_known_answers(sc, c1):
     """Every KAT section of c++/tests/lm_solver.cpp, at 1e-11 relative
@@ -91,6 +96,21 @@ def test_against_block_arrow_oracle_at_sizes_the_reference_cannot_run(name, kwar
     n = scenarios.compare_to_golden(got, want, rtol=1e-10, label="device-vs-oracle")
     assert n >= 3
     assert gs.launches() > 0
+
+
+@pytest.mark.parametrize("name,kwargs", [
+    ("C2", dict(n_sets=2, n_points=300_000, iteration_limit=3)),
+    ("C3", dict(n_sets=40, n_points=30_000, iteration_limit=3)),
+])
+def test_many_tiles_per_cta_against_the_oracle(name, kwargs, c1):
+    """Data sets long enough that every CTA of the Jacobian sweep walks several
+    tiles (both staging buffers of the warp-specialised kernel in use, data-set
+    changes in the middle of a CTA's range)."""
+    sc = dict(name=f"{name}_long", kind="workload", workload=name, kwargs=kwargs)
+    got, gs = scenarios.run(sc, backends.product_solver(), c1)
+    want, _ = scenarios.run(sc, backends.oracle_solver(2), c1, n_threads=_host_threads())
+    n = scenarios.compare_to_golden(got, want, rtol=1e-10, label="device-vs-oracle")
+    assert n >= 3
 
 
 def test_full_size_c3_invariants(c1):
@@ -199,11 +219,6 @@ def _consistency_checks(s, n_iterations):
         want = a["lambda_"] / 10.0 if a["decision"] == 0 else a["lambda_"] * 10.0
         assert b["lambda_"] == want
     np.testing.assert_allclose(s.chi2(), acc[-1]["new_chi2"], rtol=1e-13)
-
-
-def _host_threads():
-    import os
-    return max(1, min(os.cpu_count() or 1, 32))
 
 
 @pytest.mark.parametrize("name,kwargs,what", [
