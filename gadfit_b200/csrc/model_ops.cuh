@@ -107,8 +107,9 @@ struct ModelOpsImpl final : ModelOps
     using WsShape = JacobianWsShape<Model>;
     int occupancy[3] { 1, 1, 1 };
     bool device_ready { false };
-    // GADFIT_B200_JAC=legacy: the round-1 Jacobian sweep (every warp both
-    // evaluates and contracts), kept for A/B measurements
+    // GADFIT_B200_JAC=sp: the software-pipelined Jacobian sweep (every warp
+    // evaluates tile t + 1 while it contracts tile t) instead of the
+    // warp-specialised one; A/B measurements
     bool legacy_jacobian { false };
 
     auto init_device() -> void override
@@ -146,7 +147,7 @@ struct ModelOpsImpl final : ModelOps
         configure_ws(k_jacobian_ws<Model, true, false>);
         configure_ws(k_jacobian_ws<Model, true, true>);
         const char* jac { std::getenv("GADFIT_B200_JAC") };
-        legacy_jacobian = jac != nullptr && std::strcmp(jac, "legacy") == 0;
+        legacy_jacobian = jac != nullptr && std::strcmp(jac, "sp") == 0;
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model>, kThreads, 0));
         if (legacy_jacobian) {

@@ -249,8 +249,11 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
             }
             __syncthreads();
             if constexpr (HasPrepare<Model, ValueCtx>) {
-                if (tid == 0) {
-                    s_prep = prepare_of(Model {}, ValueCtx { s_par, a.status });
+                if (tid < 32) { // one warp, a table entry per lane (fit_function.h: tabulate)
+                    ValueCtx pc { s_par, a.status };
+                    pc.prep_lane = tid;
+                    pc.prep_lanes = 32;
+                    store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
                 }
                 __syncthreads();
             }
@@ -325,6 +328,41 @@ __device__ __forceinline__ void dense_gradient(const SDual<M>& f, double (&g)[NP
     static_for<0, NP>([&](auto K) { g[K] = f.template tangent<K>(); });
 }
 
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor path (SASS: DMMA.884)
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
+{
+    asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// --------------------------------- Jacobian, software-pipelined per warp
+//
+// One thread per point evaluates f and its gradient (static-sparsity forward
+// mode); each WARP contracts its own 32 rows on the FP64 tensor path
+// (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4): for every k-step of 4 points, lane l
+// loads J[point l%4][column 8b + l/4] for the NB column blocks -- the same
+// register is the A fragment (J^T, 8 x 4) of block row b and the B fragment
+// (J, 4 x 8) of block column b -- and issues one DMMA per upper-triangle block.
+//
+// The two jobs of a warp are SOFTWARE-PIPELINED: while the rows of tile t are
+// contracted out of staging buffer `cur`, the same warp evaluates its point of
+// tile t+1 in registers and stores the new row into buffer `cur ^ 1` afterwards.
+// The evaluation (dependent DFMA chains: exp, polynomials, tangents) and the
+// contraction (48 DMMA in 6 independent accumulator chains for 21 columns)
+// are independent instruction streams inside one basic block, so the hardware
+// always has something from the other stream to issue while one waits on a
+// result -- both share the FP64 datapath, which is the resource to keep busy.
+// A warp only reads rows it wrote itself: the steady state has __syncwarp()
+// only, no block-wide or named barrier.  Accumulators (2 doubles per block
+// and lane) stay in registers across all tiles of a data set; the 8 warps are
+// summed in fixed order when the data set changes.  128 registers per thread,
+// two CTAs per SM.
+//
+// If J_out != nullptr the weighted Jacobian rows are stored parameter-major
+// (J_out[k * n_points + i]) for the omega sweep and getJacobian(); if
+// r_out != nullptr so are the weighted residuals (kStore instantiation only).
 template <class Model>
 struct JacobianShape
 {
@@ -335,44 +373,30 @@ struct JacobianShape
     // upper triangle of M has NBT blocks of 8 x 8
     static constexpr int NB { (NA + 7) / 8 };
     static constexpr int NBT { NB * (NB + 1) / 2 };
-    // Staging buffer, column major: A[column][point], leading dimension
+    // Staging buffers, column major: A[column][point], leading dimension
     // kTile + 4 so that the DMMA fragment loads are bank-conflict free
     // ((row * LDP + point) mod 16 distinct over a half warp)
     static constexpr int LDP { kTile + 4 };
     static constexpr int kWarps { kThreads / 32 };
-    static constexpr size_t stage_doubles { static_cast<size_t>(NB) * 8 * LDP };
-    static constexpr size_t flush_doubles { static_cast<size_t>(kWarps) * NBT * 64 };
+    using Pre = prepared_t<Model, GradCtx>;
+    // dynamic shared memory, in doubles: two staging buffers of NA column
+    // lines, one all-zero line (padding columns of the last block), the
+    // scratch of the cross-warp sum, input prefetch, parameters, prepare()
+    static constexpr size_t stage { static_cast<size_t>(NA) * LDP };
+    static constexpr size_t zero_line { LDP };
+    static constexpr size_t flush { static_cast<size_t>(kWarps) * NBT * 64 };
+    static constexpr size_t prefetch { 2 * 3 * kTile };
+    static constexpr size_t par { (NP + 1) & ~size_t { 1 } };
+    static constexpr size_t prep { (sizeof(Pre) + 7) / 8 };
+    // the flush scratch aliases the staging buffers (used only between runs)
+    static constexpr size_t work { 2 * stage > flush ? 2 * stage : flush };
     static constexpr size_t smem_bytes {
-        sizeof(double) * (stage_doubles > flush_doubles ? stage_doubles : flush_doubles)
+        sizeof(double) * (work + zero_line + prefetch + par + prep)
     };
 };
 
-// D(8x8) += A(8x4) * B(4x8), FP64 tensor path (SASS: DMMA.884)
-__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, const double b)
-{
-    asm volatile(
-      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(c[0]), "+d"(c[1])
-      : "d"(a), "d"(b));
-}
-
-// One thread per point evaluates f and its gradient (static-sparsity forward
-// mode) and writes its augmented row, column major, into the staging buffer.
-// Each WARP then contracts its own 32 rows on the FP64 tensor path:
-// for every k-step of 4 points, lane l loads J[point l%4][column 8b + l/4] for
-// the NB column blocks -- the same register is the A fragment (J^T, 8 x 4) of
-// block row b and the B fragment (J, 4 x 8) of block column b -- and issues
-// one DMMA per upper-triangle block.  A warp only reads what it wrote itself,
-// so the steady state needs __syncwarp() only; the accumulators (2 doubles per
-// block and lane) stay in registers across all tiles of a data set and the 8
-// warps are summed in fixed order when the data set changes.
-// If J_out != nullptr the weighted Jacobian rows are stored parameter-major
-// (J_out[k * n_points + i]) for the omega sweep and getJacobian(); if
-// r_out != nullptr so are the weighted residuals.
-// kStore: also write the weighted rows / residuals (J_out, r_out); the plain
-// instantiation carries neither the pointers nor the branches.
 template <class Model, bool kStore, bool kLinearLoss>
-__global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
+__global__ void __launch_bounds__(kThreads, 2)
   k_jacobian(const SweepArgs a,
              const int loss_type,
              const int* __restrict__ slot_base,
@@ -382,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
              const long long n_points)
 {
     using Shape = JacobianShape<Model>;
+    using Pre = typename Shape::Pre;
     constexpr int NP { Shape::NP };
     constexpr int NA { Shape::NA };
     constexpr int NT { Shape::NT };
@@ -389,14 +414,29 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
     constexpr int NBT { Shape::NBT };
     constexpr int LDP { Shape::LDP };
     constexpr int kWarps { Shape::kWarps };
-    extern __shared__ double s_A[]; // [NB * 8][LDP], reused by flush()
-    __shared__ double s_par[NP];
+    extern __shared__ double s_dyn[];
+    double* const s_stage { s_dyn };                       // [2][NA][LDP], reused by flush()
+    double* const s_zero { s_stage + Shape::work };        // [LDP]
+    double* const s_pre { s_zero + Shape::zero_line };     // [2][3][kTile]
+    double* const s_par { s_pre + Shape::prefetch };       // [NP]
+    Pre* const s_prep { reinterpret_cast<Pre*>(s_par + Shape::par) };
 
     const int tid { static_cast<int>(threadIdx.x) };
     const int lane { tid & 31 };
     const int warp { tid >> 5 };
     const int frag_row { lane >> 2 }; // column within a block of 8
     const int frag_pt { lane & 3 };   // point within a k-step of 4
+    for (int i = tid; i < LDP; i += kThreads) {
+        s_zero[i] = 0.0;
+    }
+    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
+                                    / gridDim.x) };
+    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
+                                    * (blockIdx.x + 1) / gridDim.x) };
+    if (t0 >= t1) {
+        return;
+    }
+    int slot { slot_base[blockIdx.x] };
 
     double acc[NBT][2];
 #pragma unroll
@@ -404,26 +444,12 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
         acc[b][0] = 0.0;
         acc[b][1] = 0.0;
     }
-    const auto zero_padding { [&]() {
-        for (int idx = tid; idx < (NB * 8 - NA) * LDP; idx += kThreads) {
-            s_A[NA * LDP + idx] = 0.0;
-        }
-    } };
-    zero_padding();
-
-    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
-                                    / gridDim.x) };
-    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
-                                    * (blockIdx.x + 1) / gridDim.x) };
-    int slot { slot_base[blockIdx.x] };
-    int cur_set { -1 };
-
     // Sum the warps in fixed order and write one partial (packed triangle)
     const auto flush { [&]() {
-        __syncthreads();
+        __syncthreads(); // every warp is done with the staging buffers
 #pragma unroll
         for (int b = 0; b < NBT; ++b) {
-            double* dst { s_A + (warp * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
+            double* dst { s_stage + (warp * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
             dst[0] = acc[b][0];
             dst[1] = acc[b][1];
             acc[b][0] = 0.0;
@@ -443,109 +469,96 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
             double total { 0.0 };
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
-                total += s_A[(w * NBT + blk) * 64 + within];
+                total += s_stage[(w * NBT + blk) * 64 + within];
             }
             partials[static_cast<long long>(slot) * NT + e] = total;
         }
         __syncthreads();
-        zero_padding();
         ++slot;
     } };
 
-    // Software pipeline: x, y, sigma of the NEXT tile are copied asynchronously
-    // (LDGSTS) into a double-buffered shared staging area before the current
-    // tile is evaluated, so the DRAM latency hides behind a whole tile of work
-    // without holding registers.  Every thread reads back only what it
-    // requested itself: cp.async.wait_group is the only synchronisation.
-    __shared__ double s_pre[2][3][kTile];
-    TileWalker walk {};
-    if (t0 < t1) {
-        walk.seek(a, t0);
-    }
-    const auto prefetch { [&](const TileWalker& w, const int t, const int buf) {
+    // x, y, 1/sigma of the tile after next are copied asynchronously (LDGSTS)
+    // into a double-buffered staging area: the DRAM latency hides behind a
+    // whole tile of work without holding registers.  Every thread reads back
+    // only what it requested itself.
+    const auto prefetch { [&](const TileWalker& w, const int t, const int slot_in) {
         if (tid < w.len(t)) {
             const long long i { w.off(t) + tid };
-            cp_async_8(&s_pre[buf][0][tid], a.x + i);
-            cp_async_8(&s_pre[buf][1][tid], a.y + i);
-            cp_async_8(&s_pre[buf][2][tid], a.inv_sig + i);
+            double* dst { s_pre + slot_in * 3 * kTile + tid };
+            cp_async_8(dst, a.x + i);
+            cp_async_8(dst + kTile, a.y + i);
+            cp_async_8(dst + 2 * kTile, a.inv_sig + i);
         }
         cp_async_commit();
     } };
-    if (t0 < t1) {
-        prefetch(walk, t0, 0);
-    }
-    int buf { 0 };
-
-    for (int t = t0; t < t1; ++t, buf ^= 1) {
-        walk.advance_to(a, t);
-        if (walk.set != cur_set) {
-            if (cur_set >= 0) {
-                flush();
-            }
-            __syncthreads();
-            if (tid < NP) {
-                s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
-            }
-            __syncthreads();
-            cur_set = walk.set;
-        }
-        const int len { walk.len(t) };
-        const long long tile_off { walk.off(t) };
-        cp_async_wait_all();
-        const double px { s_pre[buf][0][tid] };
-        const double py { s_pre[buf][1][tid] };
-        const double inv_sig { s_pre[buf][2][tid] };
-        if (t + 1 < t1) {
-            TileWalker next { walk };
-            next.advance_to(a, t + 1);
-            prefetch(next, t + 1, buf ^ 1);
-        }
-        if (warp * 32 >= len) {
-            continue; // nothing for this warp in a tail tile
-        }
-        double* column { s_A + tid };
-        if (tid < len) {
-            const long long i { tile_off + tid };
-            const auto f { evaluate(Model {}, GradCtx { s_par, a.status }, px) };
-            // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
-            const double res { (py - f.val) * inv_sig };
-            // Linear loss (the default): the row scale 1/sigma is known before
-            // f is, so tangents can leave the registers as soon as they are
-            // final instead of waiting for the residual
-            const double w { kLinearLoss ? 1.0 : loss_weight(loss_type, res) };
-            const double scale { kLinearLoss ? inv_sig : w * inv_sig };
-            double g[NP];
-            dense_gradient<NP>(f, g);
+    // The augmented row of this thread's point of tile t, in registers
+    struct Row
+    {
+        double v[NA];
+    };
+    const auto evaluate_row { [&](const TileWalker& w, const int t, const int in_slot) -> Row {
+        const bool in_range { tid < w.len(t) };
+        const double* in { s_pre + in_slot * 3 * kTile + tid };
+        // threads past the end of the data set evaluate a harmless point and
+        // contribute a zero row (no divergence inside the pipelined block)
+        const double px { in_range ? in[0] : 0.0 };
+        const double py { in_range ? in[kTile] : 0.0 };
+        const double inv_sig { in_range ? in[2 * kTile] : 0.0 };
+        const auto f { evaluate_prepared(Model {}, GradCtx { s_par, a.status }, *s_prep, px) };
+        // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
+        const double res { (py - f.val) * inv_sig };
+        const double wgt { kLinearLoss ? 1.0 : loss_weight(loss_type, res) };
+        const double scale { kLinearLoss ? inv_sig : wgt * inv_sig };
+        double g[NP];
+        dense_gradient<NP>(f, g);
+        Row row;
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                const double jk { g[k] * scale };
-                column[k * LDP] = jk;
-                if constexpr (kStore) {
-                    if (J_out != nullptr) {
-                        J_out[static_cast<long long>(k) * n_points + i] = jk;
+        for (int k = 0; k < NP; ++k) {
+            row.v[k] = in_range ? g[k] * scale : 0.0;
+        }
+        row.v[NP] = in_range ? wgt * res : 0.0;
+        if constexpr (kStore) {
+            if (in_range) {
+                const long long i { w.off(t) + tid };
+                if (J_out != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        J_out[static_cast<long long>(k) * n_points + i] = row.v[k];
                     }
                 }
-            }
-            column[NP * LDP] = w * res;
-            if constexpr (kStore) {
                 if (r_out != nullptr) {
-                    r_out[i] = w * res;
+                    r_out[i] = row.v[NP];
                 }
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NA; ++k) {
-                column[k * LDP] = 0.0;
-            }
         }
-        __syncwarp();
-        const double* frag_src { s_A + frag_row * LDP + warp * 32 + frag_pt };
+        return row;
+    } };
+    const auto store_row { [&](const Row& row, const int buf) {
+        double* column { s_stage + buf * Shape::stage + tid };
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            column[k * LDP] = row.v[k];
+        }
+    } };
+    // 8 k-steps of 4 points over this warp's 32 rows of staging buffer `buf`
+    const int frag_in_line { warp * 32 + frag_pt };
+    const bool last_is_padding { 8 * (NB - 1) + frag_row >= NA };
+    const auto contract { [&](const int buf) {
+        const double* stage { s_stage + buf * Shape::stage };
+        const double* frag_src[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
+        }
+        if (last_is_padding) {
+            frag_src[NB - 1] = s_zero + frag_in_line;
+        }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             double frag[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                frag[b] = frag_src[b * 8 * LDP + ks * 4];
+                frag[b] = frag_src[b][ks * 4];
             }
 #pragma unroll
             for (int bi = 0; bi < NB; ++bi) {
@@ -555,9 +568,61 @@ __global__ void __launch_bounds__(kThreads, kJacobianMinBlocks)
                 }
             }
         }
+    } };
+
+    TileWalker walk {};
+    walk.seek(a, t0);
+    prefetch(walk, t0, 0);
+    int t { t0 };
+    while (t < t1) {
+        // ---- a run of tiles of one data set
+        walk.advance_to(a, t);
+        __syncthreads(); // everyone is done with the previous parameters
+        if (tid < NP) {
+            s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
+        }
+        __syncthreads();
+        if constexpr (HasPrepare<Model, GradCtx>) {
+            if (tid < 32) { // one warp, a table entry per lane
+                GradCtx pc { s_par, a.status };
+                pc.prep_lane = tid;
+                pc.prep_lanes = 32;
+                store_prepared(prepare_of(Model {}, pc), *s_prep, tid, 32);
+            }
+            __syncthreads();
+        }
+        const int run_end { min(t1, walk.tile_end) };
+        // prologue: the first tile of the run is evaluated on its own
+        int in_slot { (t - t0) & 1 };
+        cp_async_wait_all();
+        if (t + 1 < t1) {
+            TileWalker next { walk };
+            next.advance_to(a, t + 1);
+            prefetch(next, t + 1, in_slot ^ 1);
+        }
+        int cur { 0 };
+        store_row(evaluate_row(walk, t, in_slot), cur);
         __syncwarp();
-    }
-    if (cur_set >= 0) {
+        for (; t < run_end; ++t) {
+            if (t + 1 < run_end) {
+                // steady state: evaluate tile t + 1 (registers only) while tile
+                // t is contracted, then publish the new row
+                in_slot ^= 1;
+                cp_async_wait_all();
+                if (t + 2 < t1) {
+                    TileWalker next { walk };
+                    next.advance_to(a, t + 2);
+                    prefetch(next, t + 2, in_slot ^ 1);
+                }
+                const Row row { evaluate_row(walk, t + 1, in_slot) };
+                contract(cur);
+                store_row(row, cur ^ 1);
+            } else {
+                contract(cur); // last tile of the run: drain
+            }
+            __syncwarp();
+            cur ^= 1;
+        }
         flush();
     }
 }
@@ -697,8 +762,11 @@ __global__ void __launch_bounds__(kJacThreads, 2)
                 }
                 named_bar_sync(kBarEval, kTile);
                 if constexpr (HasPrepare<Model, GradCtx>) {
-                    if (tid == 0) {
-                        *s_prep = prepare_of(Model {}, GradCtx { s_par, a.status });
+                    if (tid < 32) { // one warp, a table entry per lane
+                        GradCtx pc { s_par, a.status };
+                        pc.prep_lane = tid;
+                        pc.prep_lanes = 32;
+                        store_prepared(prepare_of(Model {}, pc), *s_prep, tid, 32);
                     }
                     named_bar_sync(kBarEval, kTile);
                 }
@@ -910,8 +978,11 @@ __global__ void __launch_bounds__(kThreads)
             }
             __syncthreads();
             if constexpr (HasPrepare<Model, Dir2Ctx>) {
-                if (tid == 0) {
-                    s_prep = prepare_of(Model {}, Dir2Ctx { s_par, s_seed, a.status });
+                if (tid < 32) {
+                    Dir2Ctx pc { s_par, s_seed, a.status };
+                    pc.prep_lane = tid;
+                    pc.prep_lanes = 32;
+                    store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
                 }
                 __syncthreads();
             }

@@ -94,6 +94,10 @@ struct ValueCtx : QuadratureMixin
 {
     const double* p;
     unsigned* status; // sweep-wide status word (device memory) or nullptr
+    // cooperative prepare(): this thread fills the table entries
+    // i = prep_lane, prep_lane + prep_lanes, ... (tabulate() below)
+    int prep_lane { 0 };
+    int prep_lanes { 1 };
     GADFIT_HD explicit ValueCtx(const double* p, unsigned* status = nullptr)
       : p { p }, status { status }
     {}
@@ -129,6 +133,8 @@ struct GradCtx : QuadratureMixin
 {
     const double* p;
     unsigned* status;
+    int prep_lane { 0 };
+    int prep_lanes { 1 };
     GADFIT_HD explicit GradCtx(const double* p, unsigned* status = nullptr)
       : p { p }, status { status }
     {}
@@ -169,6 +175,8 @@ struct Dir2Ctx : QuadratureMixin
     // Direction: delta1 of the column this parameter maps to, 0 if passive
     const double* seed;
     unsigned* status;
+    int prep_lane { 0 };
+    int prep_lanes { 1 };
     GADFIT_HD Dir2Ctx(const double* p, const double* seed, unsigned* status = nullptr)
       : p { p }, seed { seed }, status { status }
     {}
@@ -208,6 +216,95 @@ GADFIT_HD auto par(const Ctx& c)
 }
 
 // ---- prepare hook ----------------------------------------------------------
+//
+// Tables inside what prepare() returns: tabulate<N>(c, f) = { f(0), ..., f(N-1) }.
+// On the device the sweeps run prepare() on the 32 lanes of one warp at once:
+// each lane evaluates only the entries i = lane (mod 32) of every table (so a
+// table of exp() at 15 quadrature nodes costs one exp() of latency, not 15)
+// and store_prepared() below merges the lanes' parts in shared memory.
+// Contexts without prep_lane / prep_lanes members (the reference's AdVar, the
+// oracle's dual) fill the whole table.
+template <class T, int N>
+struct Table
+{
+    T v[N];
+    GADFIT_HD const T& operator[](const int i) const { return v[i]; }
+};
+
+template <int N, class Ctx, class F>
+GADFIT_HD auto tabulate(const Ctx& c, F&& f)
+{
+    using T = decltype(f(0));
+    Table<T, N> t;
+    if constexpr (requires { c.prep_lane; }) {
+        for (int i = c.prep_lane; i < N; i += c.prep_lanes) {
+            t.v[i] = f(i);
+        }
+    } else {
+        for (int i = 0; i < N; ++i) {
+            t.v[i] = f(i);
+        }
+    }
+    return t;
+}
+
+// dst <- the part of `mine` this lane is responsible for: its entries of every
+// Table, everything else from lane 0 (every lane computed the same value)
+template <class T>
+GADFIT_HD void store_prepared(const T& mine, T& dst, const int lane, const int)
+{
+    if (lane == 0) {
+        dst = mine;
+    }
+}
+template <class T, int N>
+GADFIT_HD void store_prepared(const Table<T, N>& mine, Table<T, N>& dst, const int lane, const int lanes)
+{
+    for (int i = lane; i < N; i += lanes) {
+        dst.v[i] = mine.v[i];
+    }
+}
+// A heterogeneous aggregate for what prepare() returns: pack(a, b, c) keeps
+// each value in its own AD type (SDual masks differ), get<I>() reads it back.
+template <class... Ts>
+struct Pack;
+template <>
+struct Pack<>
+{};
+template <class T, class... Ts>
+struct Pack<T, Ts...>
+{
+    T head;
+    Pack<Ts...> tail;
+    template <int I>
+    GADFIT_HD const auto& get() const
+    {
+        if constexpr (I == 0) {
+            return head;
+        } else {
+            return tail.template get<I - 1>();
+        }
+    }
+};
+GADFIT_HD Pack<> pack()
+{
+    return {};
+}
+template <class T, class... Ts>
+GADFIT_HD Pack<T, Ts...> pack(const T& v, const Ts&... rest)
+{
+    return { v, pack(rest...) };
+}
+
+template <class T, class... Ts>
+GADFIT_HD void store_prepared(const Pack<T, Ts...>& mine, Pack<T, Ts...>& dst, const int lane, const int lanes)
+{
+    store_prepared(mine.head, dst.head, lane, lanes);
+    if constexpr (sizeof...(Ts) > 0) {
+        store_prepared(mine.tail, dst.tail, lane, lanes);
+    }
+}
+
 template <class Model, class Ctx>
 concept HasPrepare = requires(const Model& m, const Ctx& c) { m.prepare(c); };
 

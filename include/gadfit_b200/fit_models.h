@@ -23,42 +23,6 @@
 #include <tuple>
 #include <utility>
 
-namespace gadfit_b200 {
-
-// A heterogeneous aggregate for what prepare() returns: pack(a, b, c) keeps
-// each value in its own AD type (SDual masks differ), get<I>() reads it back.
-template <class... Ts>
-struct Pack;
-template <>
-struct Pack<>
-{};
-template <class T, class... Ts>
-struct Pack<T, Ts...>
-{
-    T head;
-    Pack<Ts...> tail;
-    template <int I>
-    GADFIT_HD const auto& get() const
-    {
-        if constexpr (I == 0) {
-            return head;
-        } else {
-            return tail.template get<I - 1>();
-        }
-    }
-};
-GADFIT_HD Pack<> pack()
-{
-    return {};
-}
-template <class T, class... Ts>
-GADFIT_HD Pack<T, Ts...> pack(const T& v, const Ts&... rest)
-{
-    return { v, pack(rest...) };
-}
-
-} // namespace gadfit_b200
-
 namespace gadfit_b200::models {
 
 // c++/tests/lm_solver.cpp:11-19 (also c++/tests/example.cpp:11-19)
@@ -147,30 +111,17 @@ struct ConvExpGauss
     static constexpr double upper_bound { 10.0 };
     static constexpr double sqrt_pi { 1.7724538509055160272981674833411451 };
 
-    // Parameter-only factors of the integrand: e^{-t_i/tau} at the 15 nodes,
-    // 1/sg and the normalisation 1/(sg sqrt(pi))
-    template <class Decay, class InvSg, class Norm>
-    struct Prepared
-    {
-        Decay decay[k15_size];
-        InvSg inv_sg;
-        Norm norm;
-    };
+    // Parameter-only factors of the integrand: e^{-t_i/tau} at the 15 nodes
+    // (get<0>), 1/sg (get<1>) and the normalisation 1/(sg sqrt(pi)) (get<2>)
     template <class Ctx>
     GADFIT_HD auto prepare(const Ctx& c) const
     {
         const auto tau { par<1>(c) };
         const auto sg { par<2>(c) };
-        using Decay = decltype(exp(-1.0 / tau));
-        using InvSg = decltype(1.0 / sg);
-        using Norm = decltype(1.0 / (sg * sqrt_pi));
-        Prepared<Decay, InvSg, Norm> pre;
-        for (int i = 0; i < k15_size; ++i) {
-            pre.decay[i] = exp(-kronrod_node(i, 0.0, upper_bound) / tau);
-        }
-        pre.inv_sg = 1.0 / sg;
-        pre.norm = 1.0 / (sg * sqrt_pi);
-        return pre;
+        return pack(tabulate<k15_size>(
+                      c, [&](const int i) { return exp(-kronrod_node(i, 0.0, upper_bound) / tau); }),
+                    1.0 / sg,
+                    1.0 / (sg * sqrt_pi));
     }
     template <class Ctx, class Pre>
     GADFIT_HD auto operator()(const Ctx& c, const Pre& pre, const double x) const
@@ -178,8 +129,8 @@ struct ConvExpGauss
         const auto t0 { par<3>(c) };
         const auto integral { c.kronrod_indexed(
           0.0, upper_bound, [&](const auto& t, const int i) {
-              const auto z { (x - t - t0) * pre.inv_sg };
-              return pre.decay[i] * exp(-(z * z)) * pre.norm;
+              const auto z { (x - t - t0) * pre.template get<1>() };
+              return pre.template get<0>()[i] * exp(-(z * z)) * pre.template get<2>();
           }) };
         return par<0>(c) * integral + par<4>(c);
     }
@@ -197,40 +148,33 @@ struct LorentzDoubleInt
 
     // The exponential factorises, e^{-k1 u^2 - k2 v^2} = e^{-k1 u^2} e^{-k2 v^2},
     // and each factor depends on the parameters and ONE node index only: 30
-    // exponentials per data set instead of 225 per data point
-    template <class E1, class E2, class G2>
-    struct Prepared
-    {
-        E1 e1[k15_size]; // e^{-k1 u_i^2}, u_i = inner node i
-        E2 e2[k15_size]; // e^{-k2 v_j^2}, v_j = outer node j
-        G2 g2;           // gamma^2
-    };
+    // exponentials per data set instead of 225 per data point.
+    // get<0>: e^{-k1 u_i^2} (inner node i), get<1>: e^{-k2 v_j^2} (outer node
+    // j), get<2>: gamma^2
     template <class Ctx>
     GADFIT_HD auto prepare(const Ctx& c) const
     {
         const auto g { par<2>(c) };
         const auto k1 { par<5>(c) };
         const auto k2 { par<6>(c) };
-        using E1 = decltype(exp(-(k1 * 1.0)));
-        using E2 = decltype(exp(-(k2 * 1.0)));
-        Prepared<E1, E2, decltype(g * g)> pre;
-        for (int i = 0; i < k15_size; ++i) {
+        const auto node_sq { [](const int i) {
             const double node { kronrod_node(i, 0.0, 1.0) };
-            pre.e1[i] = exp(-(k1 * (node * node)));
-            pre.e2[i] = exp(-(k2 * (node * node)));
-        }
-        pre.g2 = g * g;
-        return pre;
+            return node * node;
+        } };
+        return pack(tabulate<k15_size>(c, [&](const int i) { return exp(-(k1 * node_sq(i))); }),
+                    tabulate<k15_size>(c, [&](const int i) { return exp(-(k2 * node_sq(i))); }),
+                    g * g);
     }
     template <class Ctx, class Pre>
     GADFIT_HD auto operator()(const Ctx& c, const Pre& pre, const double x) const
     {
         const auto dx { x - par<1>(c) };
-        const auto lorentz { par<0>(c) * pre.g2 / (dx * dx + pre.g2) };
+        const auto& g2 { pre.template get<2>() };
+        const auto lorentz { par<0>(c) * g2 / (dx * dx + g2) };
         const auto integral { c.kronrod2d_indexed(
           0.0, 1.0, 0.0, 1.0, [&](const auto& u, const auto& v, const int i, const int j) {
               const auto s { x - u - v };
-              return pre.e1[i] * pre.e2[j] / (1.0 + s * s);
+              return pre.template get<0>()[i] * pre.template get<1>()[j] / (1.0 + s * s);
           }) };
         return lorentz + par<3>(c) + par<4>(c) * integral;
     }

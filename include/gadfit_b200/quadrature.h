@@ -131,17 +131,24 @@ GADFIT_HD auto kronrod2d_indexed(const double outer_lower,
     const double outer_shift { (outer_lower + outer_upper) / 2 };
     const double inner_scale { (inner_upper - inner_lower) / 2 };
     const double inner_shift { (inner_lower + inner_upper) / 2 };
-    auto sum { (k15_weight(0) * k15_weight(0))
-               * f(Passive { inner_scale * k15_root(0) + inner_shift },
-                   Passive { outer_scale * k15_root(0) + outer_shift },
-                   0,
-                   0) };
+    // Partially unrolled: the node evaluations of one group are independent
+    // (only the additions into `sum` are ordered), which is what lets a
+    // thread overlap their dependent FP64 chains (reciprocal, exp)
+    const Passive u0 { inner_scale * k15_root(0) + inner_shift };
+    const double w0 { k15_weight(0) };
+    auto sum { (w0 * w0) * f(u0, Passive { outer_scale * k15_root(0) + outer_shift }, 0, 0) };
+#pragma unroll 7
+    for (int j = 1; j < k15_size; ++j) {
+        sum = sum
+              + (w0 * k15_weight(j))
+                  * f(u0, Passive { outer_scale * k15_root(j) + outer_shift }, 0, j);
+    }
 #pragma unroll 1
-    for (int i = 0; i < k15_size; ++i) {
+    for (int i = 1; i < k15_size; ++i) {
         const Passive u { inner_scale * k15_root(i) + inner_shift };
         const double wi { k15_weight(i) };
-#pragma unroll 1
-        for (int j = (i == 0 ? 1 : 0); j < k15_size; ++j) {
+#pragma unroll 5
+        for (int j = 0; j < k15_size; ++j) {
             sum = sum
                   + (wi * k15_weight(j))
                       * f(u, Passive { outer_scale * k15_root(j) + outer_shift }, i, j);
@@ -284,7 +291,8 @@ GADFIT_HD auto kronrod_indexed(const double lower, const double upper, F&& f)
     const double scale { (upper - lower) / 2 };
     const double shift { (lower + upper) / 2 };
     auto sum { Rule::weight(0) * f(Passive { scale * Rule::root(0) + shift }, 0) };
-#pragma unroll 1
+    // partially unrolled: independent node evaluations overlap their FP64 chains
+#pragma unroll 7
     for (int i = 1; i < Rule::size; ++i) {
         sum = sum + Rule::weight(i) * f(Passive { scale * Rule::root(i) + shift }, i);
     }
