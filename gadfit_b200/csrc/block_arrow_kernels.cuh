@@ -29,25 +29,6 @@
 
 namespace gadfit_b200 {
 
-// Device-resident state of the LM iteration (lambda schedule and accept /
-// reject logic of lm_solver.cpp:438-501 live here, not on the host)
-struct LmState
-{
-    double lambda;
-    double old_chi2;
-    double new_chi2;
-    double acc_ratio;
-    int decision;   // 0 accept, 1 retry, 2 give up (gadfit_b200_trial)
-    int i_lambda;   // consecutive rejections in this iteration
-    int use_delta2; // acceleration passed the ratio test
-    // Status bits raised by kernels during the fit (never cleared by them):
-    // bit 0 (fit_function.h k_status_workspace): an adaptive integrator ran
-    // out of panels; bit 1: a peer-memory collective timed out
-    unsigned flags;
-};
-constexpr unsigned kFlagWorkspace { 1U };
-constexpr unsigned kFlagPeerTimeout { 2U };
-
 // Per-data-set factorisation kept between the Schur step and the
 // back-substitution of the same trial
 template <int NP>
@@ -722,21 +703,8 @@ static __global__ void k_decide(const int lambda_incs,
         return;
     }
     LmState s { *state };
-    LmState rec { s };
-    if (s.new_chi2 < s.old_chi2) {
-        s.lambda /= lambda_down;
-        s.old_chi2 = s.new_chi2;
-        s.decision = 0;
-        s.i_lambda = 0;
-    } else if (s.i_lambda < lambda_incs) {
-        s.lambda *= lambda_up;
-        s.decision = 1;
-        s.i_lambda += 1;
-    } else {
-        s.decision = 2;
-        s.i_lambda = 0;
-    }
-    rec.decision = s.decision;
+    LmState rec;
+    decide_trial(s, rec, lambda_incs, lambda_down, lambda_up);
     *state = s;
     *record = rec;
 }
@@ -796,6 +764,7 @@ struct SmallSolveArgs
     int has_locals;     // some data set has local parameters (Schur step needed)
     int update;         // apply delta1 to the parameters (no acceleration)
     int damp_max;
+    int gated;          // device-driven loop: `prepare` and whether to run at all come from state->phase
     const double* jac_partials;
     const int* slot_first;
     const int* slot_count;
@@ -871,17 +840,28 @@ __device__ __forceinline__ void cluster_barrier()
 // + column sums, k_shared_solve, k_local_backsolve, k_update_parameters
 template <int NP>
 __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThreads)
-  k_solve_small(const SmallSolveArgs a)
+  k_solve_small(const SmallSolveArgs a_in)
 {
     constexpr int NA { NP + 1 };
     constexpr int NT { NA * (NA + 1) / 2 };
     constexpr int cluster_threads { kSmallCtas * kSmallThreads };
     constexpr int sets_per_pass { kSmallCtas * kSmallSetThreads };
+    SmallSolveArgs a { a_in };
+    if (a.gated != 0) {
+        const int phase { a.state->phase };
+        if (phase == kPhaseDone) {
+            return; // the whole cluster, before any barrier
+        }
+        a.prepare = phase == kPhaseNewIteration ? 1 : 0;
+    }
     __shared__ double s_L[kMaxShared][kMaxShared + 1];
     const int tid { static_cast<int>(threadIdx.x) };
     const int cta { static_cast<int>(blockIdx.x) }; // grid == one cluster
     const int g { cta * kSmallThreads + tid };
     const int n_par { a.n_sets * NP };
+    if (a.gated != 0 && a.prepare != 0 && g == 0) {
+        a.state->n_jacobians += 1; // a Jacobian sweep ran in this slot
+    }
     const int chunks { (a.n_sets + kColumnChunk - 1) / kColumnChunk };
     // the data set this thread owns in the first pass (threads >= 128: none)
     const int my_set { tid < kSmallSetThreads ? cta * kSmallSetThreads + tid : a.n_sets };
@@ -1013,21 +993,8 @@ static __global__ void __launch_bounds__(kThreads)
     if (threadIdx.x == 0) {
         LmState s { *state };
         s.new_chi2 = total;
-        LmState rec { s };
-        if (s.new_chi2 < s.old_chi2) {
-            s.lambda /= lambda_down;
-            s.old_chi2 = s.new_chi2;
-            s.decision = 0;
-            s.i_lambda = 0;
-        } else if (s.i_lambda < lambda_incs) {
-            s.lambda *= lambda_up;
-            s.decision = 1;
-            s.i_lambda += 1;
-        } else {
-            s.decision = 2;
-            s.i_lambda = 0;
-        }
-        rec.decision = s.decision;
+        LmState rec;
+        decide_trial(s, rec, lambda_incs, lambda_down, lambda_up);
         state[0] = s;
         state[1] = rec;
         s_decision = s.decision;

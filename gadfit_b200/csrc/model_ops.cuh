@@ -24,8 +24,13 @@ struct ModelOps
     // bookkeeping of the solver works without a GPU)
     virtual auto init_device() -> void = 0;
 
-    virtual auto chi2(int grid, cudaStream_t st, const SweepArgs& a, double* partials) const
-      -> void = 0;
+    // fin.state != nullptr: the last CTA also finishes the trial step
+    // (device-driven loop, sweep_kernels.cuh: TrialFinish)
+    virtual auto chi2(int grid,
+                      cudaStream_t st,
+                      const SweepArgs& a,
+                      double* partials,
+                      const TrialFinish& fin) const -> void = 0;
     virtual auto jacobian(int grid,
                           cudaStream_t st,
                           const SweepArgs& a,
@@ -107,10 +112,9 @@ struct ModelOpsImpl final : ModelOps
     using WsShape = JacobianWsShape<Model>;
     int occupancy[3] { 1, 1, 1 };
     bool device_ready { false };
-    // GADFIT_B200_JAC=sp: the software-pipelined Jacobian sweep (every warp
-    // evaluates tile t + 1 while it contracts tile t) instead of the
-    // warp-specialised one; A/B measurements
-    bool legacy_jacobian { false };
+    // true: the software-pipelined Jacobian sweep (every warp evaluates tile
+    // t + 1 while it contracts tile t); false: the warp-specialised one
+    bool pipelined_jacobian { false };
 
     auto init_device() -> void override
     {
@@ -146,11 +150,23 @@ struct ModelOpsImpl final : ModelOps
         configure_ws(k_jacobian_ws<Model, false, true>);
         configure_ws(k_jacobian_ws<Model, true, false>);
         configure_ws(k_jacobian_ws<Model, true, true>);
+        // Which Jacobian sweep (sweep_kernels.cuh).  Measured on B200 (r02c):
+        // with several 8-column blocks the contraction dominates and dedicated
+        // contraction warps win (config 2, 21 columns: 2.52 vs 2.62 ms); with a
+        // single block the evaluation dominates and the software-pipelined
+        // kernel, whose warps all evaluate with 128 registers, wins (config 4:
+        // 0.90 vs 1.25 ms; config 5: 8.7 vs 8.9 ms).  GADFIT_B200_JAC=ws|sp
+        // overrides the choice (A/B runs).
         const char* jac { std::getenv("GADFIT_B200_JAC") };
-        legacy_jacobian = jac != nullptr && std::strcmp(jac, "sp") == 0;
+        pipelined_jacobian = Shape::NB < 2;
+        if (jac != nullptr && std::strcmp(jac, "sp") == 0) {
+            pipelined_jacobian = true;
+        } else if (jac != nullptr && std::strcmp(jac, "ws") == 0) {
+            pipelined_jacobian = false;
+        }
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model>, kThreads, 0));
-        if (legacy_jacobian) {
+        if (pipelined_jacobian) {
             GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
               &occupancy[1], k_jacobian<Model, true, false>, kThreads, Shape::smem_bytes));
         } else {
@@ -177,10 +193,13 @@ struct ModelOpsImpl final : ModelOps
         return sizeof(LocalFactor<NP>);
     }
 
-    auto chi2(const int grid, cudaStream_t st, const SweepArgs& a, double* partials) const
-      -> void override
+    auto chi2(const int grid,
+              cudaStream_t st,
+              const SweepArgs& a,
+              double* partials,
+              const TrialFinish& fin) const -> void override
     {
-        k_chi2<Model><<<grid, kThreads, 0, st>>>(a, partials);
+        k_chi2<Model><<<grid, kThreads, 0, st>>>(a, partials, fin);
     }
     auto jacobian(const int grid,
                   cudaStream_t st,
@@ -194,7 +213,7 @@ struct ModelOpsImpl final : ModelOps
     {
         const bool store { J_out != nullptr || r_out != nullptr };
         const bool linear { loss == GADFIT_B200_LOSS_LINEAR };
-        if (!legacy_jacobian) {
+        if (!pipelined_jacobian) {
             const auto launch { [&](auto* kernel) {
                 kernel<<<grid, kJacThreads, WsShape::smem_bytes, st>>>(
                   a, loss, slot_base, partials, J_out, r_out, n_points);

@@ -232,6 +232,10 @@ struct SolverImpl
     DeviceBuffer<unsigned char> d_factors;
     DeviceBuffer<double> d_J, d_resid, d_omega;
     DeviceBuffer<LmState> d_state;  // [0] live state, [1] record, [2] copy
+    DeviceBuffer<gadfit_b200_trial> d_trace; // device-driven loop: one record per trial
+    DeviceBuffer<unsigned> d_chi2_counter;   //   CTAs of the chi2 sweep that are done
+    gadfit_b200_trial* h_trace { nullptr };  // pinned, kTraceBatch records
+    static constexpr int kTraceBatch { 64 };
     DeviceBuffer<double> d_scratch;
     LmState* h_mirror { nullptr };  // pinned, 2 entries: record, state
     double* h_scalar { nullptr };   // pinned
@@ -264,6 +268,9 @@ struct SolverImpl
         }
         if (h_scalar != nullptr) {
             cudaFreeHost(h_scalar);
+        }
+        if (h_trace != nullptr) {
+            cudaFreeHost(h_trace);
         }
         if (stream != nullptr) {
             cudaStreamDestroy(stream);
@@ -417,6 +424,8 @@ struct SolverImpl
         GADFIT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         GADFIT_CUDA_TRY(cudaMallocHost(&h_mirror, 2 * sizeof(LmState)));
         GADFIT_CUDA_TRY(cudaMallocHost(&h_scalar, 24 * sizeof(double)));
+        GADFIT_CUDA_TRY(cudaMallocHost(&h_trace, kTraceBatch * sizeof(gadfit_b200_trial)));
+        d_chi2_counter.zero(1, stream);
         ops->init_device();
         d_state.zero(3, stream);
         d_scratch.ensure(8);
@@ -645,7 +654,7 @@ struct SolverImpl
     [[nodiscard]] auto sweep_args() const -> SweepArgs
     {
         return { d_x.ptr, d_y.ptr,      d_sig.ptr, d_set_tile_begin.ptr, d_set_point_begin.ptr,
-                 n_local_sets, n_tiles, d_par.ptr, &d_state.ptr->flags };
+                 n_local_sets, n_tiles, d_par.ptr, &d_state.ptr->flags, nullptr, 0 };
     }
 
     // --------------------------------------------------------------- phases
@@ -655,7 +664,7 @@ struct SolverImpl
     {
         t_chi2.start(stream);
         if (n_tiles > 0) {
-            ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr);
+            ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr, TrialFinish {});
             launched();
             if (world > 1 && peer.active) {
                 // final sum of the CTA partials and the all-reduce in one kernel
@@ -993,21 +1002,30 @@ struct SolverImpl
         launched();
     }
 
-    auto solve_small(const bool first_trial) -> void
+    // Work arrays of k_solve_small (once per iteration; once per fit in the
+    // device-driven loop)
+    auto prepare_small_buffers() -> void
+    {
+        const int VG { shared_len() };
+        const int chunks { (n_local_sets + kColumnChunk - 1) / kColumnChunk };
+        d_contrib.ensure(2 * static_cast<size_t>(n_local_sets) * std::max(VG, 2));
+        d_stage.ensure(
+          std::max(d_stage.capacity, 2 * static_cast<size_t>(chunks) * std::max(VG, 1)));
+        d_shared_sums.ensure(std::max(VG, 1));
+        if (n_active > pg) {
+            d_schur_sums.ensure(std::max(VG, 1));
+        } else {
+            d_schur_sums.zero(std::max(VG, 1), stream);
+        }
+    }
+
+    auto solve_small(const bool first_trial, const bool gated = false) -> void
     {
         const int VG { shared_len() };
         const int chunks { (n_local_sets + kColumnChunk - 1) / kColumnChunk };
         t_linalg.start(stream);
-        if (first_trial) {
-            d_contrib.ensure(2 * static_cast<size_t>(n_local_sets) * std::max(VG, 2));
-            d_stage.ensure(
-              std::max(d_stage.capacity, 2 * static_cast<size_t>(chunks) * std::max(VG, 1)));
-            d_shared_sums.ensure(std::max(VG, 1));
-            if (n_active > pg) {
-                d_schur_sums.ensure(std::max(VG, 1));
-            } else {
-                d_schur_sums.zero(std::max(VG, 1), stream);
-            }
+        if (first_trial && !gated) {
+            prepare_small_buffers();
         }
         SmallSolveArgs a {};
         a.n_sets = n_local_sets;
@@ -1018,6 +1036,7 @@ struct SolverImpl
         a.has_locals = n_active > pg ? 1 : 0;
         a.update = 1;
         a.damp_max = settings.damp_max;
+        a.gated = gated ? 1 : 0;
         a.jac_partials = d_jac_partials.ptr;
         a.slot_first = slots_jac.first.ptr;
         a.slot_count = slots_jac.count.ptr;
@@ -1047,7 +1066,7 @@ struct SolverImpl
     auto chi2_decide_small() -> void
     {
         t_chi2.start(stream);
-        ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr);
+        ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr, TrialFinish {});
         k_finish_trial<<<1, kThreads, 0, stream>>>(d_chi2_partials.ptr,
                                                    grid_chi2,
                                                    settings.lambda_incs,
@@ -1059,6 +1078,105 @@ struct SolverImpl
                                                    d_par.ptr);
         launched(2);
         t_chi2.stop(stream);
+    }
+
+    // ---- device-driven loop (latency-bound regime) ---------------------------
+    //
+    // The host-driven loop reads one small record per trial step to know what
+    // to enqueue next: a stream synchronisation (~15 us) and an idle GPU until
+    // the next launch arrives, per trial.  Here the decision stays on the
+    // device: a TRIAL SLOT is the fixed launch sequence
+    //     Jacobian sweep | k_solve_small | chi2 sweep (+ finish in its last CTA)
+    // whose kernels look at LmState::phase and skip themselves (Jacobian sweep
+    // unless a new iteration starts, everything once the fit is done), the
+    // last CTA of the chi2 sweep takes the accept / reject decision, reverts
+    // the parameters, writes the trace record and sets the phase of the next
+    // slot.  The host enqueues as many slots as there are iterations left (the
+    // number needed if every step is accepted) and only then reads the state.
+    // Same kernels, same sums: results are bit-identical to the host-driven
+    // loop (GADFIT_B200_DEVICE_LOOP=0).
+    [[nodiscard]] auto device_loop_allowed() const -> bool
+    {
+        const char* e { std::getenv("GADFIT_B200_DEVICE_LOOP") };
+        if (e != nullptr && std::strcmp(e, "0") == 0) {
+            return false;
+        }
+        // per-iteration text output needs the parameters on the host after
+        // every accepted step: host-driven loop
+        const bool chatty { log_fn != nullptr && !io_test(io_hide_all) && !io_test(io_final_only) };
+        return !chatty;
+    }
+
+    auto enqueue_trial_slot() -> void
+    {
+        SweepArgs sweep { sweep_args() };
+        sweep.gate = d_state.ptr;
+        // Jacobian sweep: only when a new iteration starts
+        sweep.gate_skip = (1 << kPhaseRetry) | (1 << kPhaseDone);
+        t_jacobian.start(stream);
+        ops->jacobian(slots_jac.grid, stream, sweep, settings.loss, slots_jac.base.ptr,
+                      d_jac_partials.ptr, nullptr, nullptr, n_local_points);
+        t_jacobian.stop(stream);
+        launched();
+        solve_small(true, true);
+        sweep.gate_skip = 1 << kPhaseDone;
+        TrialFinish fin {};
+        fin.state = d_state.ptr;
+        fin.counter = d_chi2_counter.ptr;
+        fin.lambda_incs = settings.lambda_incs;
+        fin.iteration_limit = settings.iteration_limit;
+        fin.lambda_down = settings.lambda_down;
+        fin.lambda_up = settings.lambda_up;
+        fin.n_par = static_cast<long long>(n_local_sets) * NP;
+        fin.par_old = d_par_old.ptr;
+        fin.par = d_par.ptr;
+        fin.trace = d_trace.ptr;
+        fin.trace_cap = static_cast<int>(d_trace.capacity);
+        t_chi2.start(stream);
+        ops->chi2(grid_chi2, stream, sweep, d_chi2_partials.ptr, fin);
+        t_chi2.stop(stream);
+        launched();
+    }
+
+    // Returns the final state; fills `trace`
+    auto run_device_loop() -> LmState
+    {
+        const long long worst { static_cast<long long>(settings.iteration_limit)
+                                * (settings.lambda_incs + 1) };
+        d_trace.ensure(static_cast<size_t>(std::min<long long>(std::max<long long>(worst, 1), 1 << 20)));
+        prepare_small_buffers();
+        int n_read { 0 };
+        LmState now {};
+        int iterations_left { settings.iteration_limit };
+        while (true) {
+            const int n_slots { std::max(1, std::min(iterations_left, kTraceBatch)) };
+            for (int k = 0; k < n_slots; ++k) {
+                enqueue_trial_slot();
+            }
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(
+              h_mirror, d_state.ptr, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
+            const int n_copy { static_cast<int>(std::min<size_t>(
+              n_slots, d_trace.capacity - std::min<size_t>(n_read, d_trace.capacity))) };
+            if (n_copy > 0) {
+                GADFIT_CUDA_TRY(cudaMemcpyAsync(h_trace,
+                                                d_trace.ptr + n_read,
+                                                n_copy * sizeof(gadfit_b200_trial),
+                                                cudaMemcpyDeviceToHost,
+                                                stream));
+            }
+            GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
+            now = h_mirror[0];
+            const int n_new { std::min(now.n_trials - n_read, n_copy) };
+            for (int k = 0; k < n_new; ++k) {
+                trace.push_back(h_trace[k]);
+            }
+            n_read += std::max(n_new, 0);
+            if (now.flags != 0U || now.phase == kPhaseDone) {
+                break;
+            }
+            iterations_left = settings.iteration_limit - (now.iteration - 1);
+        }
+        return now;
     }
 
     // The initial values of the damping matrix (lm_solver.cpp:414,424-428)
@@ -1304,6 +1422,8 @@ struct SolverImpl
         LmState init {};
         init.lambda = lambda0;
         init.use_delta2 = 0;
+        init.phase = kPhaseNewIteration;
+        init.iteration = 1;
         GADFIT_CUDA_TRY(cudaMemcpyAsync(
           d_state.ptr, &init, sizeof(LmState), cudaMemcpyHostToDevice, stream));
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1319,6 +1439,33 @@ struct SolverImpl
         int i_iteration { 0 };
         bool finished { settings.iteration_limit == 0 };
         bool finite_start { true };
+        int device_loop_trials { -1 };
+        int device_loop_jacobians { 0 };
+        if (small && !finished && device_loop_allowed()) {
+            const LmState end { run_device_loop() };
+            device_loop_trials = end.n_trials;
+            device_loop_jacobians = end.n_jacobians;
+            i_iteration = end.iteration;
+            lambda = end.lambda;
+            last_old_chi2 = end.old_chi2;
+            lambda_lhs = trace.empty() ? lambda0 : trace.back().lambda;
+            if (end.flags != 0U) {
+                t_main.stop(stream);
+                n_iterations = std::max(i_iteration - 1, 0);
+                download_parameters();
+                fitted = true;
+                throw_if_flagged(end.flags);
+            }
+            if (!trace.empty() && trace.back().decision == 2) { // lm_solver.cpp:482-494
+                --i_iteration;
+                stop_reason = std::isfinite(trace.back().old_chi2)
+                                ? GADFIT_B200_STOP_LAMBDA_INCS
+                                : GADFIT_B200_STOP_NON_FINITE_CHI2;
+            } else if (!io_test(io_hide_all)) { // lm_solver.cpp:497-499
+                log_line("Iteration limit reached");
+            }
+            finished = true;
+        }
         while (!finished) {
             ++i_iteration;
             if (small) {
@@ -1411,6 +1558,13 @@ struct SolverImpl
         for (PhaseTimer* t :
              { &t_jacobian, &t_chi2, &t_linalg, &t_omega, &t_main, &t_jac_kernel }) {
             t->collect();
+        }
+        if (device_loop_trials >= 0) {
+            // slots that skipped themselves were timed too (a few microseconds
+            // each); the call counts are those of the work that ran
+            t_jacobian.calls = device_loop_jacobians;
+            t_linalg.calls = device_loop_trials;
+            t_chi2.calls = device_loop_trials + 1;
         }
         fitted = true;
         // lm_solver.cpp:504-510

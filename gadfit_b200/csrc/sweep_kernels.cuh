@@ -23,11 +23,84 @@
 // results are bitwise reproducible run to run.
 #pragma once
 
+#include "gadfit_b200.h"
 #include "gadfit_b200/fit_models.h"
 
 #include <cuda_runtime.h>
 
 namespace gadfit_b200 {
+
+// Device-resident state of the LM loop (lm_solver.cpp:441-502: lambda, the
+// chi2 pair of the accept test, the decision of the last trial step)
+struct LmState
+{
+    double lambda;
+    double old_chi2;
+    double new_chi2;
+    double acc_ratio;
+    int decision;   // 0 accept, 1 retry, 2 give up (gadfit_b200_trial)
+    int i_lambda;   // consecutive rejections in this iteration
+    int use_delta2; // acceleration passed the ratio test
+    // Status bits raised by kernels during the fit (never cleared by them):
+    // bit 0 (fit_function.h k_status_workspace): an adaptive integrator ran
+    // out of panels; bit 1: a peer-memory collective timed out
+    unsigned flags;
+    // Device-driven loop (latency-bound regime): what the next trial slot has
+    // to do -- the kernels of a slot read it and skip themselves
+    int phase;       // kPhaseNewIteration / kPhaseRetry / kPhaseDone
+    int iteration;   // 1-based number of the iteration in progress
+    int n_trials;    // trial records written to the device trace
+    int n_jacobians; // Jacobian sweeps that actually ran
+};
+constexpr unsigned kFlagWorkspace { 1U };
+constexpr unsigned kFlagPeerTimeout { 2U };
+constexpr int kPhaseNewIteration { 0 }; // Jacobian sweep + first solve of an iteration
+constexpr int kPhaseRetry { 1 };        // re-solve with the raised lambda
+constexpr int kPhaseDone { 2 };         // nothing left to do
+
+// The accept / reject step of lm_solver.cpp:455-494; `rec` = the state before
+// the decision + the decision (what the reference prints, :457)
+__device__ __forceinline__ void decide_trial(LmState& s,
+                                             LmState& rec,
+                                             const int lambda_incs,
+                                             const double lambda_down,
+                                             const double lambda_up)
+{
+    rec = s;
+    if (s.new_chi2 < s.old_chi2) {
+        s.lambda /= lambda_down;
+        s.old_chi2 = s.new_chi2;
+        s.decision = 0;
+        s.i_lambda = 0;
+    } else if (s.i_lambda < lambda_incs) {
+        s.lambda *= lambda_up;
+        s.decision = 1;
+        s.i_lambda += 1;
+    } else {
+        s.decision = 2;
+        s.i_lambda = 0;
+    }
+    rec.decision = s.decision;
+}
+
+// What the LAST CTA of a chi2 sweep needs to finish the trial step itself
+// (device-driven loop): final sum of the CTA partials in fixed order, accept /
+// reject, revert of the parameters, trace record, phase of the next slot.
+// state == nullptr: plain sweep, partials only.
+struct TrialFinish
+{
+    LmState* state;
+    unsigned* counter; // CTAs of this sweep that have written their partial
+    int lambda_incs;
+    int iteration_limit;
+    double lambda_down;
+    double lambda_up;
+    long long n_par;
+    const double* par_old;
+    double* par;
+    gadfit_b200_trial* trace;
+    int trace_cap;
+};
 
 constexpr int kTile { 256 };    // points per tile == threads per CTA
 constexpr int kThreads { 256 };
@@ -71,7 +144,16 @@ struct SweepArgs
     // Status word of the sweep (LmState::flags): bit 0 = an adaptive
     // integrator ran out of panels (fit_function.h, k_status_workspace)
     unsigned* status;
+    // Device-driven loop: the sweep returns at once if bit (gate->phase) of
+    // gate_skip is set (nullptr: never)
+    const LmState* gate;
+    int gate_skip;
 };
+
+__device__ __forceinline__ bool sweep_is_gated_off(const SweepArgs& a)
+{
+    return a.gate != nullptr && ((a.gate_skip >> a.gate->phase) & 1) != 0;
+}
 
 // Walks the tiles of a CTA in ascending order.  Offsets and lengths are
 // arithmetic; memory is touched only when the data set changes.
@@ -194,6 +276,71 @@ __device__ __forceinline__ double loss_weight(const int loss_type, const double 
     }
 }
 
+// Thread 0 of the CTA that finishes a trial: decision, trace record, phase of
+// the next slot.  Returns the decision.
+__device__ __forceinline__ int finish_trial_record(const TrialFinish& fin, const double new_chi2)
+{
+    LmState s { *fin.state };
+    s.new_chi2 = new_chi2;
+    LmState rec;
+    decide_trial(s, rec, fin.lambda_incs, fin.lambda_down, fin.lambda_up);
+    if (fin.trace != nullptr) {
+        if (s.n_trials < fin.trace_cap) {
+            fin.trace[s.n_trials] = { rec.lambda, rec.new_chi2, rec.old_chi2, s.iteration, s.decision };
+        }
+        s.n_trials += 1;
+        if (s.decision == 0) { // lm_solver.cpp:462-468, 496-501
+            if (s.iteration >= fin.iteration_limit) {
+                s.phase = kPhaseDone;
+            } else {
+                s.iteration += 1;
+                s.phase = kPhaseNewIteration;
+            }
+        } else {
+            s.phase = s.decision == 1 ? kPhaseRetry : kPhaseDone;
+        }
+    }
+    fin.state[0] = s;
+    fin.state[1] = rec;
+    return s.decision;
+}
+
+// Tail of the chi2 sweep in the device-driven loop: the CTA that writes the
+// last partial sums them all in the order of k_sum_partials / k_finish_trial
+// (so chi2 is bit-identical to the stage-wise path), decides and reverts.
+__device__ __forceinline__ void finish_trial_in_last_block(const TrialFinish& fin,
+                                                           const double* block_partials,
+                                                           double* s_red)
+{
+    __shared__ int s_last;
+    __shared__ int s_decision;
+    const int tid { static_cast<int>(threadIdx.x) };
+    if (tid == 0) {
+        __threadfence(); // my partial before my ticket
+        s_last = atomicAdd(fin.counter, 1U) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last == 0) {
+        return;
+    }
+    __threadfence();
+    double sum { 0.0 };
+    for (int i = tid; i < static_cast<int>(gridDim.x); i += kThreads) {
+        sum += __ldcg(block_partials + i);
+    }
+    const double total { block_sum(sum, s_red) };
+    if (tid == 0) {
+        *fin.counter = 0U; // ready for the next sweep
+        s_decision = finish_trial_record(fin, total);
+    }
+    __syncthreads();
+    if (s_decision != 0) { // revertParameters, lm_solver.cpp:206-218
+        for (long long i = tid; i < fin.n_par; i += kThreads) {
+            fin.par[i] = fin.par_old[i];
+        }
+    }
+}
+
 // ------------------------------------------------------------------- chi2
 //
 // sum_i ((y_i - f(x_i)) / sigma_i)^2 with passive parameters; the loss
@@ -202,8 +349,11 @@ __device__ __forceinline__ double loss_weight(const int loss_type, const double 
 // sweeps).
 template <class Model>
 __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
-  k_chi2(const SweepArgs a, double* __restrict__ block_partials)
+  k_chi2(const SweepArgs a, double* __restrict__ block_partials, const TrialFinish fin)
 {
+    if (sweep_is_gated_off(a)) {
+        return;
+    }
     constexpr int NP { Model::n_pars };
     constexpr int kChi2Unroll { Chi2Tuning<Model>::unroll };
     using Pre = prepared_t<Model, ValueCtx>;
@@ -316,6 +466,9 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
     if (threadIdx.x == 0) {
         block_partials[blockIdx.x] = total;
     }
+    if (fin.state != nullptr) {
+        finish_trial_in_last_block(fin, block_partials, s_red);
+    }
 }
 
 // --------------------------------------------------------------- Jacobian
@@ -405,6 +558,9 @@ __global__ void __launch_bounds__(kThreads, 2)
              double* __restrict__ r_out,
              const long long n_points)
 {
+    if (sweep_is_gated_off(a)) {
+        return;
+    }
     using Shape = JacobianShape<Model>;
     using Pre = typename Shape::Pre;
     constexpr int NP { Shape::NP };
@@ -481,14 +637,15 @@ __global__ void __launch_bounds__(kThreads, 2)
     // into a double-buffered staging area: the DRAM latency hides behind a
     // whole tile of work without holding registers.  Every thread reads back
     // only what it requested itself.
+    // Threads past the end of a data set's last tile fetch its last point: in
+    // the pipelined block they evaluate a VALID point (an adaptive integral
+    // over a degenerate dummy range would never converge) and zero their row.
     const auto prefetch { [&](const TileWalker& w, const int t, const int slot_in) {
-        if (tid < w.len(t)) {
-            const long long i { w.off(t) + tid };
-            double* dst { s_pre + slot_in * 3 * kTile + tid };
-            cp_async_8(dst, a.x + i);
-            cp_async_8(dst + kTile, a.y + i);
-            cp_async_8(dst + 2 * kTile, a.inv_sig + i);
-        }
+        const long long i { w.off(t) + min(tid, w.len(t) - 1) };
+        double* dst { s_pre + slot_in * 3 * kTile + tid };
+        cp_async_8(dst, a.x + i);
+        cp_async_8(dst + kTile, a.y + i);
+        cp_async_8(dst + 2 * kTile, a.inv_sig + i);
         cp_async_commit();
     } };
     // The augmented row of this thread's point of tile t, in registers
@@ -499,11 +656,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     const auto evaluate_row { [&](const TileWalker& w, const int t, const int in_slot) -> Row {
         const bool in_range { tid < w.len(t) };
         const double* in { s_pre + in_slot * 3 * kTile + tid };
-        // threads past the end of the data set evaluate a harmless point and
-        // contribute a zero row (no divergence inside the pipelined block)
-        const double px { in_range ? in[0] : 0.0 };
-        const double py { in_range ? in[kTile] : 0.0 };
-        const double inv_sig { in_range ? in[2 * kTile] : 0.0 };
+        // (threads past the end of the data set: the last point again, row
+        // zeroed below -- no divergence inside the pipelined block)
+        const double px { in[0] };
+        const double py { in[kTile] };
+        const double inv_sig { in[2 * kTile] };
         const auto f { evaluate_prepared(Model {}, GradCtx { s_par, a.status }, *s_prep, px) };
         // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
         const double res { (py - f.val) * inv_sig };
@@ -701,6 +858,9 @@ __global__ void __launch_bounds__(kJacThreads, 2)
                 double* __restrict__ r_out,
                 const long long n_points)
 {
+    if (sweep_is_gated_off(a)) {
+        return;
+    }
     using Shape = JacobianWsShape<Model>;
     using Pre = typename Shape::Pre;
     constexpr int NP { Shape::NP };

@@ -341,6 +341,31 @@ def test_fused_small_problem_path_is_bit_identical_to_the_stagewise_path(sc, c1,
             np.testing.assert_array_equal(getattr(fs, getter)(), getattr(ss, getter)())
 
 
+@pytest.mark.parametrize(
+    "sc",
+    [s for s in scenarios.ALL_SCENARIOS if not _is_accelerated(s)]
+    + [dict(name="C3_small", kind="workload", workload="C3", kwargs=dict(n_sets=300, n_points=700)),
+       dict(name="C2_small", kind="workload", workload="C2", kwargs=dict(n_sets=5, n_points=20_000))],
+    ids=lambda s: s["name"])
+def test_device_driven_loop_is_bit_identical_to_the_host_driven_loop(sc, c1, monkeypatch):
+    """Latency-bound regime: with the accept / reject decision, the revert and
+    the trace on the device (the kernels of a trial slot skip themselves by
+    LmState::phase; the host reads the state once per batch of slots) every
+    trial record and every parameter is identical to the last bit to the loop
+    that reads one record per trial."""
+    monkeypatch.setenv("GADFIT_B200_DEVICE_LOOP", "1")
+    dev, ds = scenarios.run(sc, backends.product_solver(), c1)
+    monkeypatch.setenv("GADFIT_B200_DEVICE_LOOP", "0")
+    host, hs = scenarios.run(sc, backends.product_solver(), c1)
+    assert dev["trace"] == host["trace"]
+    assert dev["chi2"] == host["chi2"]
+    assert dev["pars"] == host["pars"]
+    assert dev["iterations"] == host["iterations"]
+    assert ds.stopReason() == hs.stopReason()
+    assert ds.timings()["jacobian"][1] == hs.timings()["jacobian"][1]
+    assert ds.timings()["chi2"][1] == hs.timings()["chi2"][1]
+
+
 def test_distinct_solvers_on_concurrent_host_threads(c1):
     """SURVEY 8(b) threading row (reference doc/user_guide.tex:778): one solver
     is not re-entrant, but distinct solvers may run concurrently from different
