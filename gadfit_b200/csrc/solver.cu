@@ -235,6 +235,14 @@ struct SolverImpl
     DeviceBuffer<gadfit_b200_trial> d_trace; // device-driven loop: one record per trial
     DeviceBuffer<unsigned> d_chi2_counter;   //   CTAs of the chi2 sweep that are done
     gadfit_b200_trial* h_trace { nullptr };  // pinned, kTraceBatch records
+    // pipelined upload (upload_data(true)): copies on their own stream, the
+    // number of leading points that are complete published after every chunk
+    cudaStream_t copy_stream { nullptr };
+    cudaEvent_t upload_done { nullptr };
+    DeviceBuffer<unsigned long long> d_arrived;
+    unsigned long long* h_arrived { nullptr }; // pinned, one entry per chunk
+    size_t h_arrived_capacity { 0 };
+    bool upload_in_flight { false }; // first Jacobian sweep must wait / invert sigma
     static constexpr int kTraceBatch { 64 };
     DeviceBuffer<double> d_scratch;
     LmState* h_mirror { nullptr };  // pinned, 2 entries: record, state
@@ -271,6 +279,15 @@ struct SolverImpl
         }
         if (h_trace != nullptr) {
             cudaFreeHost(h_trace);
+        }
+        if (h_arrived != nullptr) {
+            cudaFreeHost(h_arrived);
+        }
+        if (upload_done != nullptr) {
+            cudaEventDestroy(upload_done);
+        }
+        if (copy_stream != nullptr) {
+            cudaStreamDestroy(copy_stream);
         }
         if (stream != nullptr) {
             cudaStreamDestroy(stream);
@@ -493,9 +510,92 @@ struct SolverImpl
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
     }
 
+    // x, y, sigma of the owned points in chunks of ~4M points, chunk-major
+    // (x_c, y_c, sigma_c, then the arrival counter), on the copy stream
+    auto enqueue_chunked_copies() -> void
+    {
+        if (copy_stream == nullptr) {
+            GADFIT_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            GADFIT_CUDA_TRY(cudaEventCreateWithFlags(&upload_done, cudaEventDisableTiming));
+        }
+        constexpr long long chunk_points { 1LL << 22 };
+        // pieces: (device offset, length, host pointers)
+        struct Piece
+        {
+            long long off;
+            long long n;
+            const double* x;
+            const double* y;
+            const double* e;
+        };
+        std::vector<Piece> pieces;
+        long long off { 0 };
+        for (int ls = 0; ls < n_local_sets; ++ls) {
+            const auto& set { sets[part.first + ls] };
+            for (long long done = 0; done < local_count[ls];) {
+                const long long n { std::min(chunk_points, local_count[ls] - done) };
+                const long long h { local_begin[ls] + done };
+                // extend the previous piece if host and device ranges continue it
+                if (!pieces.empty() && pieces.back().n + n <= chunk_points
+                    && pieces.back().x + pieces.back().n == set.x + h
+                    && pieces.back().y + pieces.back().n == set.y + h
+                    && pieces.back().e + pieces.back().n == set.errors + h) {
+                    pieces.back().n += n;
+                } else {
+                    pieces.push_back({ off, n, set.x + h, set.y + h, set.errors + h });
+                }
+                off += n;
+                done += n;
+            }
+        }
+        if (pieces.size() > h_arrived_capacity) {
+            if (h_arrived != nullptr) {
+                // the previous upload's counter copies have long completed
+                GADFIT_CUDA_TRY(cudaStreamSynchronize(copy_stream));
+                cudaFreeHost(h_arrived);
+                h_arrived = nullptr;
+            }
+            GADFIT_CUDA_TRY(cudaMallocHost(&h_arrived, pieces.size() * sizeof(unsigned long long)));
+            h_arrived_capacity = pieces.size();
+        }
+        d_arrived.zero(1, stream);
+        // the copies may start once the counter is zero and the buffers exist
+        GADFIT_CUDA_TRY(cudaEventRecord(upload_done, stream));
+        GADFIT_CUDA_TRY(cudaStreamWaitEvent(copy_stream, upload_done, 0));
+        for (size_t k = 0; k < pieces.size(); ++k) {
+            const Piece& p { pieces[k] };
+            const size_t bytes { static_cast<size_t>(p.n) * sizeof(double) };
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_x.ptr + p.off, p.x, bytes, cudaMemcpyHostToDevice,
+                                            copy_stream));
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_y.ptr + p.off, p.y, bytes, cudaMemcpyHostToDevice,
+                                            copy_stream));
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_sig.ptr + p.off, p.e, bytes, cudaMemcpyHostToDevice,
+                                            copy_stream));
+            h_arrived[k] = static_cast<unsigned long long>(p.off + p.n);
+            GADFIT_CUDA_TRY(cudaMemcpyAsync(d_arrived.ptr, h_arrived + k, sizeof(unsigned long long),
+                                            cudaMemcpyHostToDevice, copy_stream));
+        }
+        GADFIT_CUDA_TRY(cudaEventRecord(upload_done, copy_stream));
+    }
+
+    // After the first Jacobian sweep of a pipelined upload has been enqueued:
+    // everything later on the compute stream may assume the data are complete
+    auto finish_pipelined_upload() -> void
+    {
+        if (upload_in_flight) {
+            GADFIT_CUDA_TRY(cudaStreamWaitEvent(stream, upload_done, 0));
+            upload_in_flight = false;
+        }
+    }
+
     // Copy this rank's share of the data sets to HBM, concatenated data-set
     // major, and lay out the tiles.
-    auto upload_data() -> void
+    // pipelined (only from fit()): the copies go chunk by chunk through a copy
+    // stream of their own and are NOT waited for; the first Jacobian sweep
+    // follows the arrival counter (SweepArgs::arrived) and inverts sigma as it
+    // goes, so the sweep -- and all host-side set-up below -- overlaps the PCIe
+    // transfer.  Needs explicit errors for every owned data set.
+    auto upload_data(const bool pipelined = false) -> void
     {
         ensure_device();
         const int S { static_cast<int>(sets.size()) };
@@ -565,12 +665,26 @@ struct SolverImpl
                 ls = next;
             }
         } };
-        copy_field(0, d_x.ptr);
-        copy_field(1, d_y.ptr);
-        copy_field(2, d_sig.ptr);
-        if (n_local_points > 0) {
-            k_invert<<<blocks_for(n_local_points, 256), 256, 0, stream>>>(d_sig.ptr, n_local_points);
-            launched();
+        bool all_have_errors { n_local_points > 0 };
+        for (int ls = 0; ls < n_local_sets; ++ls) {
+            const auto& set { sets[part.first + ls] };
+            all_have_errors = all_have_errors
+                              && (local_count[ls] == 0
+                                  || (set.x != nullptr && set.y != nullptr && set.errors != nullptr));
+        }
+        upload_in_flight = false;
+        if (pipelined && all_have_errors && n_local_points >= (1LL << 21)) {
+            enqueue_chunked_copies();
+            upload_in_flight = true;
+        } else {
+            copy_field(0, d_x.ptr);
+            copy_field(1, d_y.ptr);
+            copy_field(2, d_sig.ptr);
+            if (n_local_points > 0) {
+                k_invert<<<blocks_for(n_local_points, 256), 256, 0, stream>>>(d_sig.ptr,
+                                                                              n_local_points);
+                launched();
+            }
         }
 
         // Tiles
@@ -606,10 +720,10 @@ struct SolverImpl
     }
 
     // Parameters and roles of the local data sets -> device
-    auto upload_parameters() -> void
+    auto upload_parameters(const bool pipelined = false) -> void
     {
         if (!data_uploaded) {
-            upload_data();
+            upload_data(pipelined);
         }
         const size_t n { static_cast<size_t>(n_local_sets) * NP };
         d_par.upload(par.data() + static_cast<size_t>(part.first) * NP, n, stream);
@@ -654,7 +768,8 @@ struct SolverImpl
     [[nodiscard]] auto sweep_args() const -> SweepArgs
     {
         return { d_x.ptr, d_y.ptr,      d_sig.ptr, d_set_tile_begin.ptr, d_set_point_begin.ptr,
-                 n_local_sets, n_tiles, d_par.ptr, &d_state.ptr->flags, nullptr, 0 };
+                 n_local_sets, n_tiles, d_par.ptr, &d_state.ptr->flags, nullptr, 0,
+                 upload_in_flight ? d_arrived.ptr : nullptr, upload_in_flight ? 1 : 0 };
     }
 
     // --------------------------------------------------------------- phases
@@ -1107,17 +1222,19 @@ struct SolverImpl
         return !chatty;
     }
 
-    auto enqueue_trial_slot() -> void
+    auto enqueue_trial_slot(const bool skip_jacobian = false) -> void
     {
         SweepArgs sweep { sweep_args() };
         sweep.gate = d_state.ptr;
-        // Jacobian sweep: only when a new iteration starts
-        sweep.gate_skip = (1 << kPhaseRetry) | (1 << kPhaseDone);
-        t_jacobian.start(stream);
-        ops->jacobian(slots_jac.grid, stream, sweep, settings.loss, slots_jac.base.ptr,
-                      d_jac_partials.ptr, nullptr, nullptr, n_local_points);
-        t_jacobian.stop(stream);
-        launched();
+        if (!skip_jacobian) {
+            // Jacobian sweep: only when a new iteration starts
+            sweep.gate_skip = (1 << kPhaseRetry) | (1 << kPhaseDone);
+            t_jacobian.start(stream);
+            ops->jacobian(slots_jac.grid, stream, sweep, settings.loss, slots_jac.base.ptr,
+                          d_jac_partials.ptr, nullptr, nullptr, n_local_points);
+            t_jacobian.stop(stream);
+            launched();
+        }
         solve_small(true, true);
         sweep.gate_skip = 1 << kPhaseDone;
         TrialFinish fin {};
@@ -1139,7 +1256,8 @@ struct SolverImpl
     }
 
     // Returns the final state; fills `trace`
-    auto run_device_loop() -> LmState
+    // first_jacobian_done: the sweep of the first slot already ran (pipelined upload)
+    auto run_device_loop(const bool first_jacobian_done) -> LmState
     {
         const long long worst { static_cast<long long>(settings.iteration_limit)
                                 * (settings.lambda_incs + 1) };
@@ -1151,7 +1269,7 @@ struct SolverImpl
         while (true) {
             const int n_slots { std::max(1, std::min(iterations_left, kTraceBatch)) };
             for (int k = 0; k < n_slots; ++k) {
-                enqueue_trial_slot();
+                enqueue_trial_slot(first_jacobian_done && n_read == 0 && trace.empty() && k == 0);
             }
             GADFIT_CUDA_TRY(cudaMemcpyAsync(
               h_mirror, d_state.ptr, sizeof(LmState), cudaMemcpyDeviceToHost, stream));
@@ -1404,7 +1522,13 @@ struct SolverImpl
         stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
         prepare_indexing();
         ensure_device();
-        upload_parameters();
+        // Data not in HBM yet: the copies are enqueued chunk by chunk on a copy
+        // stream and not waited for; the FIRST Jacobian sweep (launched ahead of
+        // the initial chi2 sweep: both only read the start parameters) follows
+        // their arrival, so that sweep and all the set-up below overlap the
+        // PCIe transfer.
+        const bool fresh_upload { !data_uploaded && settings.iteration_limit != 0 };
+        upload_parameters(fresh_upload);
         reset_timers();
         init_damping();
         const size_t n_par { static_cast<size_t>(std::max(n_local_sets, 1)) * NP };
@@ -1418,6 +1542,18 @@ struct SolverImpl
         have_delta2 = false;
         trace.clear();
         n_iterations = 0;
+        struct UploadGuard // an exception before the first sweep: never leave copies unwaited
+        {
+            SolverImpl* self;
+            ~UploadGuard()
+            {
+                if (self->upload_in_flight) {
+                    cudaStreamSynchronize(self->copy_stream);
+                    self->upload_in_flight = false;
+                    self->data_uploaded = false; // sigma was not inverted: upload again
+                }
+            }
+        } upload_guard { this };
 
         LmState init {};
         init.lambda = lambda0;
@@ -1433,6 +1569,12 @@ struct SolverImpl
 
         const bool small { small_path() };
         t_main.start(stream);
+        bool first_jacobian_done { false };
+        if (fresh_upload) {
+            small ? jacobian_sweep_small() : jacobian_phase(accelerate, false);
+            finish_pipelined_upload();
+            first_jacobian_done = true;
+        }
         chi2_phase(&d_state.ptr->new_chi2);
         k_copy_chi2_to_old<<<1, 1, 0, stream>>>(d_state.ptr);
         launched();
@@ -1442,7 +1584,7 @@ struct SolverImpl
         int device_loop_trials { -1 };
         int device_loop_jacobians { 0 };
         if (small && !finished && device_loop_allowed()) {
-            const LmState end { run_device_loop() };
+            const LmState end { run_device_loop(first_jacobian_done) };
             device_loop_trials = end.n_trials;
             device_loop_jacobians = end.n_jacobians;
             i_iteration = end.iteration;
@@ -1468,7 +1610,9 @@ struct SolverImpl
         }
         while (!finished) {
             ++i_iteration;
-            if (small) {
+            if (first_jacobian_done && i_iteration == 1) {
+                // already swept (ahead of the initial chi2, following the upload)
+            } else if (small) {
                 jacobian_sweep_small();
             } else {
                 jacobian_phase(accelerate, false);

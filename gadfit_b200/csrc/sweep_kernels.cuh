@@ -148,7 +148,27 @@ struct SweepArgs
     // gate_skip is set (nullptr: never)
     const LmState* gate;
     int gate_skip;
+    // Pipelined upload (first Jacobian sweep of a fit() whose data are still
+    // arriving over PCIe): `arrived` = number of leading points of x / y /
+    // sigma that are complete in HBM, written by the copy engine after every
+    // chunk (nullptr: everything is there); first_touch: `inv_sig` still holds
+    // sigma -- this sweep inverts it in place.
+    const unsigned long long* arrived;
+    int first_touch;
 };
+
+// Spin (one thread's view) until the first `need` points have arrived
+__device__ __forceinline__ void wait_arrived(const SweepArgs& a,
+                                             const long long need,
+                                             unsigned long long& seen)
+{
+    if (a.arrived == nullptr || static_cast<unsigned long long>(need) <= seen) {
+        return;
+    }
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.arrived) : "memory");
+    } while (seen < static_cast<unsigned long long>(need));
+}
 
 __device__ __forceinline__ bool sweep_is_gated_off(const SweepArgs& a)
 {
@@ -640,7 +660,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     // Threads past the end of a data set's last tile fetch its last point: in
     // the pipelined block they evaluate a VALID point (an adaptive integral
     // over a degenerate dummy range would never converge) and zero their row.
+    unsigned long long seen { 0ULL };
     const auto prefetch { [&](const TileWalker& w, const int t, const int slot_in) {
+        wait_arrived(a, w.off(t) + w.len(t), seen);
         const long long i { w.off(t) + min(tid, w.len(t) - 1) };
         double* dst { s_pre + slot_in * 3 * kTile + tid };
         cp_async_8(dst, a.x + i);
@@ -660,7 +682,13 @@ __global__ void __launch_bounds__(kThreads, 2)
         // zeroed below -- no divergence inside the pipelined block)
         const double px { in[0] };
         const double py { in[kTile] };
-        const double inv_sig { in[2 * kTile] };
+        double inv_sig { in[2 * kTile] };
+        if (a.first_touch != 0) { // pipelined upload: sigma -> 1 / sigma, in place
+            inv_sig = 1.0 / inv_sig;
+            if (in_range) {
+                const_cast<double*>(a.inv_sig)[w.off(t) + tid] = inv_sig;
+            }
+        }
         const auto f { evaluate_prepared(Model {}, GradCtx { s_par, a.status }, *s_prep, px) };
         // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
         const double res { (py - f.val) * inv_sig };
@@ -901,7 +929,9 @@ __global__ void __launch_bounds__(kJacThreads, 2)
 
     if (warp < kJacEvalWarps) {
         // ------------------------------------------------------ evaluation
+        unsigned long long seen { 0ULL };
         const auto prefetch { [&](const TileWalker& w, const int t, const int buf) {
+            wait_arrived(a, w.off(t) + w.len(t), seen);
             if (tid < w.len(t)) {
                 const long long i { w.off(t) + tid };
                 double* dst { s_pre + buf * 3 * kTile + tid };
@@ -937,7 +967,11 @@ __global__ void __launch_bounds__(kJacThreads, 2)
             cp_async_wait_all();
             const double px { s_pre[buf * 3 * kTile + tid] };
             const double py { s_pre[buf * 3 * kTile + kTile + tid] };
-            const double inv_sig { s_pre[buf * 3 * kTile + 2 * kTile + tid] };
+            double inv_sig { s_pre[buf * 3 * kTile + 2 * kTile + tid] };
+            if (a.first_touch != 0 && tid < len) { // pipelined upload: invert sigma in place
+                inv_sig = 1.0 / inv_sig;
+                const_cast<double*>(a.inv_sig)[tile_off + tid] = inv_sig;
+            }
             if (t + 1 < t1) {
                 TileWalker next { walk };
                 next.advance_to(a, t + 1);
