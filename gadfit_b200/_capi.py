@@ -88,7 +88,7 @@ NOT_AVAILABLE = 13
 TOO_MANY_PARAMETERS = 14
 
 # gadfit_b200_array
-JACOBIAN, JTJ, DTD, LEFT_SIDE, RIGHT_SIDE, RESIDUALS, INV_JTJ, DELTA1, DELTA2, OMEGA = range(10)
+JACOBIAN, JTJ, DTD, LEFT_SIDE, RIGHT_SIDE, RESIDUALS, INV_JTJ, DELTA1, DELTA2, OMEGA, INV_JTJ_DIAGONAL = range(11)
 
 # every symbol include/gadfit_b200.h declares (checked by tests/test_capi_host.py)
 CORE_SYMBOLS = [

@@ -19,6 +19,8 @@ struct ModelOps
     // Resident CTAs per SM of each sweep kernel (0: chi2, 1: Jacobian, 2: omega)
     [[nodiscard]] virtual auto ctas_per_sm(int which) const -> int = 0;
     [[nodiscard]] virtual auto factor_bytes() const -> size_t = 0;
+    // Tiles per unrolled group of the chi2 sweep (its CTA ranges are aligned to it)
+    [[nodiscard]] virtual auto chi2_unroll() const -> int = 0;
     // First device use: opt in to the shared memory the Jacobian sweep needs
     // and query occupancies (kept out of the constructor so that the host-side
     // bookkeeping of the solver works without a GPU)
@@ -192,6 +194,7 @@ struct ModelOpsImpl final : ModelOps
     {
         return sizeof(LocalFactor<NP>);
     }
+    [[nodiscard]] auto chi2_unroll() const -> int override { return Chi2Tuning<Model>::unroll; }
 
     auto chi2(const int grid,
               cudaStream_t st,

@@ -145,6 +145,147 @@ __global__ void k_dense_inverse(const int n, const double* A, double* L, double*
     }
 }
 
+// ---- block-arrow inverse of J^T J (LMsolver::getInvJTJ) ---------------------
+//
+// The reference inverts the dense n x n matrix (dpptrf + dpotri,
+// lm_solver.cpp:578-585, lapack.cpp:113-125).  Here J^T J = [G C'; C L] with L
+// block diagonal, and its inverse follows from the factors the Schur solve
+// already uses (lambda = 0):  L_s = R_s R_s',  Y_s = R_s^-1 C_s',
+// S = G - sum_s Y_s' Y_s,
+//     inv_gg       = S^-1
+//     W_s          = L_s^-1 C_s' = R_s^-T Y_s
+//     inv_sg       = -W_s inv_gg
+//     inv_ss       = L_s^-1 + W_s inv_gg W_s'
+//     inv_st (s/=t) = W_s inv_gg W_t' = -inv_sg(s) W_t'   (dense assembly only)
+// One thread per data set; the layout of a block record is
+// [ss (NP x NP) | sg (NP x NP, row i = local slot, column a = global slot) | W].
+__global__ void k_schur_matrix(const int pg,
+                               const double* __restrict__ shared_sums,
+                               const double* __restrict__ schur_sums,
+                               double* __restrict__ A)
+{
+    const int e { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (e < pg * pg) {
+        const int i { e / pg };
+        const int j { e % pg };
+        const int o { i <= j ? tri_index(pg, i, j) : tri_index(pg, j, i) };
+        A[e] = shared_sums[o] - schur_sums[o];
+    }
+}
+
+__global__ void k_inverse_local(const int NP,
+                                const int n_sets,
+                                const unsigned* __restrict__ active,
+                                const unsigned global_mask,
+                                const double* __restrict__ factors, // LocalFactor<NP> records
+                                const double* __restrict__ inv_gg,  // [pg][pg]
+                                const int pg,
+                                double* __restrict__ blocks,        // [n_sets][3 NP NP]
+                                double* __restrict__ work)          // [n_sets][NP NP]
+{
+    const int s { static_cast<int>(blockIdx.x * blockDim.x + threadIdx.x) };
+    if (s >= n_sets) {
+        return;
+    }
+    const int pl { popcount32(active[s] & ~global_mask) };
+    const long long NN { static_cast<long long>(NP) * NP };
+    const double* R { factors + s * (2 * NN + NP) };
+    const double* Y { R + NN };
+    double* ss { blocks + s * 3 * NN };
+    double* sg { ss + NN };
+    double* W { sg + NN };
+    double* T { work + s * NN }; // R^-1, lower triangular
+    for (int c = 0; c < pl; ++c) {
+        for (int i = 0; i < pl; ++i) {
+            double v { i == c ? 1.0 : 0.0 };
+            for (int k = c; k < i; ++k) {
+                v -= R[i * NP + k] * T[k * NP + c];
+            }
+            T[i * NP + c] = i < c ? 0.0 : v / R[i * NP + i];
+        }
+    }
+    // W = R^-T Y by back substitution
+    for (int a = 0; a < pg; ++a) {
+        for (int i = pl - 1; i >= 0; --i) {
+            double v { Y[i * NP + a] };
+            for (int k = i + 1; k < pl; ++k) {
+                v -= R[k * NP + i] * W[k * NP + a];
+            }
+            W[i * NP + a] = v / R[i * NP + i];
+        }
+    }
+    for (int i = 0; i < pl; ++i) {
+        for (int a = 0; a < pg; ++a) {
+            double v { 0.0 };
+            for (int b = 0; b < pg; ++b) {
+                v += W[i * NP + b] * inv_gg[b * pg + a];
+            }
+            sg[i * NP + a] = -v;
+        }
+    }
+    for (int i = 0; i < pl; ++i) {
+        for (int j = 0; j < pl; ++j) {
+            double v { 0.0 };
+            for (int k = (i > j ? i : j); k < pl; ++k) {
+                v += T[k * NP + i] * T[k * NP + j]; // L_s^-1 = R^-T R^-1
+            }
+            for (int a = 0; a < pg; ++a) {
+                v -= sg[i * NP + a] * W[j * NP + a];
+            }
+            ss[i * NP + j] = v;
+        }
+    }
+}
+
+// Dense n x n view of the block-arrow inverse; col_set[c] = data set of column
+// c (-1: shared), col_idx[c] = its slot among the shared / that set's local columns
+__global__ void k_inverse_assemble(const long long n,
+                                   const int NP,
+                                   const int pg,
+                                   const int* __restrict__ col_set,
+                                   const int* __restrict__ col_idx,
+                                   const double* __restrict__ inv_gg,
+                                   const double* __restrict__ blocks,
+                                   double* __restrict__ out)
+{
+    const long long e { static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x };
+    if (e >= n * n) {
+        return;
+    }
+    // (r, c) and (c, r) take the same path: the output is symmetric to the bit
+    const long long r { e / n <= e % n ? e / n : e % n };
+    const long long c { e / n <= e % n ? e % n : e / n };
+    const int sr { col_set[r] };
+    const int sc { col_set[c] };
+    const int ir { col_idx[r] };
+    const int ic { col_idx[c] };
+    const long long NN { static_cast<long long>(NP) * NP };
+    double v { 0.0 };
+    if (sr < 0 && sc < 0) {
+        v = inv_gg[ir * pg + ic];
+    } else if (sr < 0) {
+        v = blocks[sc * 3 * NN + NN + ic * NP + ir];
+    } else if (sc < 0) {
+        v = blocks[sr * 3 * NN + NN + ir * NP + ic];
+    } else if (sr == sc) {
+        v = blocks[sr * 3 * NN + ir * NP + ic];
+    } else {
+        const double* sg { blocks + sr * 3 * NN + NN + ir * NP };
+        const double* W { blocks + sc * 3 * NN + 2 * NN + ic * NP };
+        for (int b = 0; b < pg; ++b) {
+            v -= sg[b] * W[b];
+        }
+    }
+    out[e] = v;
+}
+
+// Tile range and first data set of every CTA of one sweep (SweepArgs::cta_*)
+struct CtaTable
+{
+    DeviceBuffer<int> tile_begin; // [grid + 1]
+    DeviceBuffer<int> first_set;  // [grid]
+};
+
 struct SlotTable
 {
     int grid { 0 };
@@ -152,6 +293,7 @@ struct SlotTable
     DeviceBuffer<int> base;  // [grid]  first slot of each CTA
     DeviceBuffer<int> first; // [n_sets] first slot of each data set
     DeviceBuffer<int> count; // [n_sets]
+    CtaTable cta;
 };
 
 } // namespace
@@ -218,6 +360,8 @@ struct SolverImpl
     int n_tiles { 0 };
     SlotTable slots_jac, slots_omega;
     int grid_chi2 { 0 };
+    CtaTable cta_chi2;
+    std::vector<int> h_set_tile_begin; // host copy of d_set_tile_begin
 
     DeviceBuffer<double> d_par, d_par_old, d_par_jac;
     DeviceBuffer<unsigned> d_active;
@@ -476,9 +620,32 @@ struct SolverImpl
         ++n_nccl_reductions;
     }
 
+    // unroll > 1: the cut points are moved up to the next multiple of `unroll`
+    // tiles counted from the start of the data set they fall into (or to its
+    // end), as k_chi2 would compute them itself
+    auto build_cta_table(CtaTable& table, const int grid, const int unroll) -> void
+    {
+        std::vector<int> begin(grid + 1, n_tiles);
+        std::vector<int> first(std::max(grid, 1), 0);
+        for (int b = 0; b < grid; ++b) {
+            int t { static_cast<int>(static_cast<long long>(n_tiles) * b / grid) };
+            if (unroll > 1 && b > 0 && t < n_tiles) {
+                const int s { h_tile_set[t] };
+                const int groups { (t - h_set_tile_begin[s] + unroll - 1) / unroll };
+                t = std::min(h_set_tile_begin[s] + groups * unroll, h_set_tile_begin[s + 1]);
+            }
+            begin[b] = t;
+            first[b] = t < n_tiles ? h_tile_set[t] : 0;
+        }
+        table.tile_begin.upload(begin, stream);
+        table.first_set.upload(first, stream);
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream)); // pageable sources die at scope exit
+    }
+
     auto build_slots(SlotTable& table, const int grid) -> void
     {
         table.grid = grid;
+        build_cta_table(table.cta, grid, 1);
         std::vector<int> base(std::max(grid, 1), 0);
         std::vector<int> first(std::max(n_local_sets, 1), 0);
         std::vector<int> count(std::max(n_local_sets, 1), 0);
@@ -698,6 +865,7 @@ struct SolverImpl
             set_point_begin[ls + 1] = set_point_begin[ls] + local_count[ls];
         }
         n_tiles = static_cast<int>(h_tile_set.size());
+        h_set_tile_begin = set_tile_begin;
         d_set_tile_begin.upload(set_tile_begin, stream);
         d_set_point_begin.upload(set_point_begin, stream);
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -708,6 +876,7 @@ struct SolverImpl
         } };
         grid_chi2 = grid_for(0);
         d_chi2_partials.ensure(grid_chi2);
+        build_cta_table(cta_chi2, grid_chi2, ops->chi2_unroll());
         build_slots(slots_jac, grid_for(1));
         build_slots(slots_omega, grid_for(2));
         const int NA { NP + 1 };
@@ -765,11 +934,13 @@ struct SolverImpl
         GADFIT_CUDA_TRY(cudaStreamSynchronize(stream));
     }
 
-    [[nodiscard]] auto sweep_args() const -> SweepArgs
+    [[nodiscard]] auto sweep_args(const CtaTable* cta = nullptr) const -> SweepArgs
     {
         return { d_x.ptr, d_y.ptr,      d_sig.ptr, d_set_tile_begin.ptr, d_set_point_begin.ptr,
                  n_local_sets, n_tiles, d_par.ptr, &d_state.ptr->flags, nullptr, 0,
-                 upload_in_flight ? d_arrived.ptr : nullptr, upload_in_flight ? 1 : 0 };
+                 upload_in_flight ? d_arrived.ptr : nullptr, upload_in_flight ? 1 : 0,
+                 cta != nullptr ? cta->tile_begin.ptr : nullptr,
+                 cta != nullptr ? cta->first_set.ptr : nullptr };
     }
 
     // --------------------------------------------------------------- phases
@@ -779,7 +950,7 @@ struct SolverImpl
     {
         t_chi2.start(stream);
         if (n_tiles > 0) {
-            ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr, TrialFinish {});
+            ops->chi2(grid_chi2, stream, sweep_args(&cta_chi2), d_chi2_partials.ptr, TrialFinish {});
             launched();
             if (world > 1 && peer.active) {
                 // final sum of the CTA partials and the all-reduce in one kernel
@@ -867,7 +1038,7 @@ struct SolverImpl
             t_jac_kernel.start(stream);
             ops->jacobian(slots_jac.grid,
                           stream,
-                          sweep_args(),
+                          sweep_args(&slots_jac.cta),
                           settings.loss,
                           slots_jac.base.ptr,
                           d_jac_partials.ptr,
@@ -982,7 +1153,7 @@ struct SolverImpl
             if (n_tiles > 0) {
                 ops->omega(slots_omega.grid,
                            stream,
-                           sweep_args(),
+                           sweep_args(&slots_omega.cta),
                            d_delta1_par.ptr,
                            d_J.ptr,
                            n_local_points,
@@ -1106,7 +1277,7 @@ struct SolverImpl
         t_jacobian.start(stream);
         ops->jacobian(slots_jac.grid,
                       stream,
-                      sweep_args(),
+                      sweep_args(&slots_jac.cta),
                       settings.loss,
                       slots_jac.base.ptr,
                       d_jac_partials.ptr,
@@ -1181,7 +1352,7 @@ struct SolverImpl
     auto chi2_decide_small() -> void
     {
         t_chi2.start(stream);
-        ops->chi2(grid_chi2, stream, sweep_args(), d_chi2_partials.ptr, TrialFinish {});
+        ops->chi2(grid_chi2, stream, sweep_args(&cta_chi2), d_chi2_partials.ptr, TrialFinish {});
         k_finish_trial<<<1, kThreads, 0, stream>>>(d_chi2_partials.ptr,
                                                    grid_chi2,
                                                    settings.lambda_incs,
@@ -1224,7 +1395,7 @@ struct SolverImpl
 
     auto enqueue_trial_slot(const bool skip_jacobian = false) -> void
     {
-        SweepArgs sweep { sweep_args() };
+        SweepArgs sweep { sweep_args(&slots_jac.cta) };
         sweep.gate = d_state.ptr;
         if (!skip_jacobian) {
             // Jacobian sweep: only when a new iteration starts
@@ -1235,6 +1406,8 @@ struct SolverImpl
             t_jacobian.stop(stream);
             launched();
         }
+        sweep = sweep_args(&cta_chi2);
+        sweep.gate = d_state.ptr;
         solve_small(true, true);
         sweep.gate_skip = 1 << kPhaseDone;
         TrialFinish fin {};
@@ -2025,6 +2198,93 @@ struct SolverImpl
         return out;
     }
 
+    // Block-arrow inverse of J^T J of the last Jacobian evaluation (kernels at
+    // the top of this file): shared block + per data set [ss | sg | W]
+    struct InverseBlocks
+    {
+        std::vector<double> gg;     // [pg][pg]
+        std::vector<double> blocks; // [S][3 NP NP]
+    };
+    DeviceBuffer<double> d_inv_gg, d_inv_blocks;
+
+    auto inverse_blocks_device() -> void
+    {
+        const int S { static_cast<int>(sets.size()) };
+        const int VG { shared_len() };
+        const size_t NN { static_cast<size_t>(NP) * NP };
+        // factors and Schur sums at lambda = 0
+        DeviceBuffer<LmState> zero_state;
+        DeviceBuffer<unsigned char> factors;
+        DeviceBuffer<double> contrib, schur, A, L, work;
+        zero_state.zero(1, stream); // lambda = 0
+        factors.ensure(static_cast<size_t>(S) * ops->factor_bytes());
+        GADFIT_CUDA_TRY(cudaMemsetAsync(factors.ptr, 0, static_cast<size_t>(S) * ops->factor_bytes(), stream));
+        contrib.ensure(static_cast<size_t>(S) * std::max(VG, 2));
+        schur.zero(std::max(VG, 1), stream);
+        if (n_active > pg) {
+            ops->local_schur(stream, d_M.ptr, d_active.ptr, global_mask, S, d_dtd_local.ptr,
+                             zero_state.ptr, factors.ptr, contrib.ptr, VG);
+            launched();
+            column_sums(contrib.ptr, VG, schur.ptr);
+        }
+        d_inv_gg.zero(std::max<size_t>(static_cast<size_t>(pg) * pg, 1), stream);
+        if (pg > 0) {
+            A.ensure(static_cast<size_t>(pg) * pg);
+            L.zero(static_cast<size_t>(pg) * pg, stream);
+            k_schur_matrix<<<blocks_for(pg * pg, 128), 128, 0, stream>>>(
+              pg, d_shared_sums.ptr, schur.ptr, A.ptr);
+            k_dense_inverse<<<1, 1, 0, stream>>>(pg, A.ptr, L.ptr, d_inv_gg.ptr);
+            launched(2);
+        }
+        d_inv_blocks.zero(static_cast<size_t>(S) * 3 * NN, stream);
+        work.zero(static_cast<size_t>(S) * NN, stream);
+        k_inverse_local<<<blocks_for(S, 128), 128, 0, stream>>>(
+          NP, S, d_active.ptr, global_mask, reinterpret_cast<const double*>(factors.ptr),
+          d_inv_gg.ptr, pg, d_inv_blocks.ptr, work.ptr);
+        launched();
+        GADFIT_CUDA_TRY(cudaStreamSynchronize(stream)); // the temporaries die here
+    }
+
+    auto inverse_blocks() -> InverseBlocks
+    {
+        inverse_blocks_device();
+        const size_t NN { static_cast<size_t>(NP) * NP };
+        return { download(d_inv_gg.ptr, static_cast<size_t>(pg) * pg),
+                 download(d_inv_blocks.ptr, sets.size() * 3 * NN) };
+    }
+
+    auto inverse_dense() -> std::vector<double>
+    {
+        const int S { static_cast<int>(sets.size()) };
+        const size_t n { static_cast<size_t>(n_active) };
+        inverse_blocks_device();
+        std::vector<int> col_set(n, -1);
+        std::vector<int> col_idx(n, 0);
+        for (int a = 0; a < pg; ++a) {
+            col_idx[a] = a;
+        }
+        for (int s = 0; s < S; ++s) {
+            const unsigned local { active[s] & ~global_mask };
+            for (int k = 0; k < NP; ++k) {
+                const long long c { column(s, k) };
+                if (c >= pg) {
+                    col_set[c] = s;
+                    col_idx[c] = slot_of(local, k);
+                }
+            }
+        }
+        DeviceBuffer<int> d_set, d_idx;
+        DeviceBuffer<double> d_out;
+        d_set.upload(col_set, stream);
+        d_idx.upload(col_idx, stream);
+        d_out.ensure(n * n);
+        k_inverse_assemble<<<blocks_for(static_cast<long long>(n * n), 256), 256, 0, stream>>>(
+          static_cast<long long>(n), NP, pg, d_set.ptr, d_idx.ptr, d_inv_gg.ptr, d_inv_blocks.ptr,
+          d_out.ptr);
+        launched();
+        return download(d_out.ptr, n * n);
+    }
+
     // Dense views of the block-arrow storage (single rank only)
     auto dense_array(const int which) -> std::vector<double>
     {
@@ -2055,6 +2315,9 @@ struct SolverImpl
             std::vector<double> out(n * n, 0.0);
             if (settings.iteration_limit == 0 && which != GADFIT_B200_DTD) {
                 return out; // fit() never computed a Jacobian
+            }
+            if (which == GADFIT_B200_INV_JTJ) {
+                return inverse_dense();
             }
             const bool want_jtj { which != GADFIT_B200_DTD };
             std::vector<double> M;
@@ -2109,18 +2372,27 @@ struct SolverImpl
                     }
                 }
             }
-            if (which == GADFIT_B200_INV_JTJ) {
-                if (n > 128) {
-                    throw StatusError { GADFIT_B200_NOT_AVAILABLE,
-                                        "dense inverse limited to n <= 128" };
+            return out;
+        }
+        case GADFIT_B200_INV_JTJ_DIAGONAL: {
+            std::vector<double> out(n, 0.0);
+            if (settings.iteration_limit == 0) {
+                return out;
+            }
+            const InverseBlocks inv { inverse_blocks() };
+            const size_t NN { static_cast<size_t>(NP) * NP };
+            for (int a = 0; a < pg; ++a) {
+                out[a] = inv.gg[static_cast<size_t>(a) * pg + a];
+            }
+            for (int s = 0; s < S; ++s) {
+                const unsigned local { active[s] & ~global_mask };
+                for (int k = 0; k < NP; ++k) {
+                    const long long c { column(s, k) };
+                    if (c >= pg) {
+                        const int i { slot_of(local, k) };
+                        out[c] = inv.blocks[static_cast<size_t>(s) * 3 * NN + static_cast<size_t>(i) * NP + i];
+                    }
                 }
-                DeviceBuffer<double> dA, dL, dI;
-                dA.upload(out, stream);
-                dL.zero(n * n, stream);
-                dI.zero(n * n, stream);
-                k_dense_inverse<<<1, 1, 0, stream>>>(static_cast<int>(n), dA.ptr, dL.ptr, dI.ptr);
-                launched();
-                out = download(dI.ptr, n * n);
             }
             return out;
         }
@@ -2186,7 +2458,7 @@ struct SolverImpl
                                             cudaMemcpyDeviceToDevice, stream));
             GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr, d_par_jac.ptr, n_par * sizeof(double),
                                             cudaMemcpyDeviceToDevice, stream));
-            ops->omega(slots_omega.grid, stream, sweep_args(), d_delta1_par.ptr, d_J.ptr,
+            ops->omega(slots_omega.grid, stream, sweep_args(&slots_omega.cta), d_delta1_par.ptr, d_J.ptr,
                        n_local_points, slots_omega.base.ptr, scratch.ptr, d_omega.ptr);
             launched();
             GADFIT_CUDA_TRY(cudaMemcpyAsync(d_par.ptr, keep.ptr, n_par * sizeof(double),
@@ -2216,7 +2488,7 @@ struct SolverImpl
             d_resid.ensure(N);
             DeviceBuffer<double> scratch;
             scratch.ensure(static_cast<size_t>(std::max(slots_jac.n_slots, 1)) * NT);
-            ops->jacobian(slots_jac.grid, stream, sweep_args(), settings.loss,
+            ops->jacobian(slots_jac.grid, stream, sweep_args(&slots_jac.cta), settings.loss,
                           slots_jac.base.ptr, scratch.ptr, d_J.ptr, d_resid.ptr,
                           n_local_points);
             launched();

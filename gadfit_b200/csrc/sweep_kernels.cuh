@@ -155,6 +155,13 @@ struct SweepArgs
     // sigma -- this sweep inverts it in place.
     const unsigned long long* arrived;
     int first_touch;
+    // Host-computed range of every CTA of THIS launch: tiles
+    // [cta_tile_begin[b], cta_tile_begin[b + 1]) and the data set of the first
+    // one.  Replaces up to three binary searches per CTA over set_tile_begin --
+    // 10 dependent global loads each for 1000 data sets, a visible share of a
+    // 30 us sweep.  nullptr: the kernel computes the range itself.
+    const int* cta_tile_begin;
+    const int* cta_first_set;
 };
 
 // Spin (one thread's view) until the first `need` points have arrived
@@ -400,15 +407,21 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
         }
         return t;
     } };
-    const int t0 { first_tile(static_cast<int>(blockIdx.x)) };
-    const int t1 { first_tile(static_cast<int>(blockIdx.x) + 1) };
+    const bool tabled { a.cta_tile_begin != nullptr };
+    const int t0 { tabled ? a.cta_tile_begin[blockIdx.x] : first_tile(static_cast<int>(blockIdx.x)) };
+    const int t1 { tabled ? a.cta_tile_begin[blockIdx.x + 1]
+                          : first_tile(static_cast<int>(blockIdx.x) + 1) };
     double sum { 0.0 };
     const int tid { static_cast<int>(threadIdx.x) };
     TileWalker walk {};
     int cur_set { -1 };
     int t { t0 };
     if (t0 < t1) {
-        walk.seek(a, t0);
+        if (tabled) {
+            walk.load(a, a.cta_first_set[blockIdx.x]);
+        } else {
+            walk.seek(a, t0);
+        }
     }
     while (t < t1) {
         walk.advance_to(a, t);
@@ -605,10 +618,13 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int i = tid; i < LDP; i += kThreads) {
         s_zero[i] = 0.0;
     }
-    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
-                                    / gridDim.x) };
-    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
-                                    * (blockIdx.x + 1) / gridDim.x) };
+    const bool tabled { a.cta_tile_begin != nullptr };
+    const int t0 { tabled ? a.cta_tile_begin[blockIdx.x]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
+                                             / gridDim.x) };
+    const int t1 { tabled ? a.cta_tile_begin[blockIdx.x + 1]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles)
+                                             * (blockIdx.x + 1) / gridDim.x) };
     if (t0 >= t1) {
         return;
     }
@@ -756,7 +772,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     } };
 
     TileWalker walk {};
-    walk.seek(a, t0);
+    if (tabled) {
+        walk.load(a, a.cta_first_set[blockIdx.x]);
+    } else {
+        walk.seek(a, t0);
+    }
     prefetch(walk, t0, 0);
     int t { t0 };
     while (t < t1) {
@@ -776,38 +796,38 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
             __syncthreads();
         }
+        const int run_begin { t };
         const int run_end { min(t1, walk.tile_end) };
-        // prologue: the first tile of the run is evaluated on its own
-        int in_slot { (t - t0) & 1 };
-        cp_async_wait_all();
-        if (t + 1 < t1) {
-            TileWalker next { walk };
-            next.advance_to(a, t + 1);
-            prefetch(next, t + 1, in_slot ^ 1);
-        }
-        int cur { 0 };
-        store_row(evaluate_row(walk, t, in_slot), cur);
-        __syncwarp();
-        for (; t < run_end; ++t) {
-            if (t + 1 < run_end) {
-                // steady state: evaluate tile t + 1 (registers only) while tile
-                // t is contracted, then publish the new row
-                in_slot ^= 1;
-                cp_async_wait_all();
-                if (t + 2 < t1) {
+        // Step k evaluates tile k + 1 (registers only) while tile k is
+        // contracted, then publishes the new row; the first step of a run
+        // (k = run_begin - 1) has nothing to contract, the last one nothing to
+        // evaluate.  ONE call site of evaluate_row: with two (a prologue of
+        // its own) the compiler turns the function body into a subroutine,
+        // and the adaptive-integral models misbehaved in it (r02e).
+        int cur { 1 }; // staging buffer being contracted; the new row goes to cur ^ 1
+        for (int k = run_begin - 1; k < run_end; ++k) {
+            const bool more { k + 1 < run_end };
+            Row row;
+            if (more) {
+                const int in_slot { (k + 1 - t0) & 1 };
+                cp_async_wait_all(); // the inputs of tile k + 1 have landed
+                if (k + 2 < t1) {
                     TileWalker next { walk };
-                    next.advance_to(a, t + 2);
-                    prefetch(next, t + 2, in_slot ^ 1);
+                    next.advance_to(a, k + 2);
+                    prefetch(next, k + 2, in_slot ^ 1);
                 }
-                const Row row { evaluate_row(walk, t + 1, in_slot) };
+                row = evaluate_row(walk, k + 1, in_slot);
+            }
+            if (k >= run_begin) {
                 contract(cur);
+            }
+            if (more) {
                 store_row(row, cur ^ 1);
-            } else {
-                contract(cur); // last tile of the run: drain
             }
             __syncwarp();
             cur ^= 1;
         }
+        t = run_end;
         flush();
     }
 }
@@ -843,6 +863,88 @@ constexpr int kJacEvalWarps { 8 };
 constexpr int kJacMmaWarps { 4 };
 constexpr int kJacThreads { (kJacEvalWarps + kJacMmaWarps) * 32 };
 static_assert(kJacEvalWarps * 32 == kTile);
+
+// Diagonal 8 x 8 blocks of M_s need only their upper triangle: on the tensor
+// path 28 of their 64 products are the mirror image of the other 36 (and the
+// last block multiplies padding columns), 40 % of all DMMA work for 21
+// columns.  With two or more column blocks the diagonal blocks are therefore
+// accumulated entry by entry on the FP64 FMA pipe (same datapath, no waste)
+// and only the off-diagonal blocks stay on DMMA: 21 columns cost 3 x 64 + 87
+// = 279 FMA per point instead of 6 x 64 = 384.
+//
+// DiagEntries<NA>: the upper-triangle entries (i <= j) of all diagonal blocks
+// in block order, row major within a block.
+template <int NA>
+struct DiagEntries
+{
+    static constexpr int NB { (NA + 7) / 8 };
+    static constexpr int count { [] {
+        int n { 0 };
+        for (int b = 0; b < NB; ++b) {
+            const int w { NA - 8 * b < 8 ? NA - 8 * b : 8 };
+            n += w * (w + 1) / 2;
+        }
+        return n;
+    }() };
+    struct Table
+    {
+        signed char row[count > 0 ? count : 1];
+        signed char col[count > 0 ? count : 1];
+    };
+    static constexpr Table table { [] {
+        Table t {};
+        int e { 0 };
+        for (int b = 0; b < NB; ++b) {
+            const int w { NA - 8 * b < 8 ? NA - 8 * b : 8 };
+            for (int i = 0; i < w; ++i) {
+                for (int j = i; j < w; ++j) {
+                    t.row[e] = static_cast<signed char>(8 * b + i);
+                    t.col[e] = static_cast<signed char>(8 * b + j);
+                    ++e;
+                }
+            }
+        }
+        return t;
+    }() };
+    // contraction warp m of W owns the entries [begin(m), begin(m + 1))
+    static constexpr int begin(const int m, const int W) { return count * m / W; }
+    static constexpr int per_warp(const int W) { return (count + W - 1) / W; }
+    // does warp m read column c?
+    static constexpr bool reads(const int m, const int W, const int c)
+    {
+        for (int e = begin(m, W); e < begin(m + 1, W); ++e) {
+            if (table.row[e] == c || table.col[e] == c) {
+                return true;
+            }
+        }
+        return false;
+    }
+};
+
+// Off-diagonal block (bi < bj) -> 0 .. NB (NB - 1) / 2 - 1, row major
+__host__ __device__ constexpr int off_block_index(const int NB, const int bi, const int bj)
+{
+    return tri_index(NB, bi, bj) - (bi + 1);
+}
+
+// One pass of the diagonal entries of contraction warp M over 32 points: lane
+// l holds the row of point l (column-major staging line `sp` = stage + point)
+template <int NA, int M, int W, int LDP, int N>
+__device__ __forceinline__ void diag_fma_pass(const double* __restrict__ sp, double (&dacc)[N])
+{
+    using D = DiagEntries<NA>;
+    double col[NA];
+    static_for<0, NA>([&](auto C) {
+        if constexpr (D::reads(M, W, C)) {
+            col[C] = sp[C * LDP];
+        }
+    });
+    static_for<D::begin(M, W), D::begin(M + 1, W)>([&](auto E) {
+        constexpr int i { D::table.row[E] };
+        constexpr int j { D::table.col[E] };
+        dacc[E - D::begin(M, W)] = ::fma(col[i], col[j], dacc[E - D::begin(M, W)]);
+    });
+}
 
 template <class Model>
 struct JacobianWsShape
@@ -916,15 +1018,22 @@ __global__ void __launch_bounds__(kJacThreads, 2)
     }
     __syncthreads();
 
-    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
-                                    / gridDim.x) };
-    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
-                                    * (blockIdx.x + 1) / gridDim.x) };
+    const bool tabled { a.cta_tile_begin != nullptr };
+    const int t0 { tabled ? a.cta_tile_begin[blockIdx.x]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
+                                             / gridDim.x) };
+    const int t1 { tabled ? a.cta_tile_begin[blockIdx.x + 1]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles)
+                                             * (blockIdx.x + 1) / gridDim.x) };
     if (t0 >= t1) {
         return;
     }
     TileWalker walk {};
-    walk.seek(a, t0);
+    if (tabled) {
+        walk.load(a, a.cta_first_set[blockIdx.x]);
+    } else {
+        walk.seek(a, t0);
+    }
     int cur_set { -1 };
 
     if (warp < kJacEvalWarps) {
@@ -1026,87 +1135,227 @@ __global__ void __launch_bounds__(kJacThreads, 2)
         // padding columns of the last block read the all-zero line instead
         const int frag_in_line { 64 * m + frag_pt };
         const bool last_is_padding { 8 * (NB - 1) + frag_row >= NA };
-        double acc[NBT][2];
-#pragma unroll
-        for (int b = 0; b < NBT; ++b) {
-            acc[b][0] = 0.0;
-            acc[b][1] = 0.0;
-        }
         int slot { slot_base[blockIdx.x] };
-        // Sum the contraction warps in fixed order, one partial (packed triangle)
-        const auto flush { [&]() {
+        if constexpr (NB >= 2) {
+            // ---- hybrid: off-diagonal blocks on DMMA (this warp's 64 rows),
+            // diagonal entries on DFMA (this warp's share of the entries, all
+            // 256 rows of the tile, lane = point)
+            using Diag = DiagEntries<NA>;
+            constexpr int NBO { NB * (NB - 1) / 2 };
+            constexpr int kDiagPerWarp { Diag::per_warp(kJacMmaWarps) };
+            double acc[NBO][2];
+            double dacc[kDiagPerWarp];
 #pragma unroll
-            for (int b = 0; b < NBT; ++b) {
-                double* dst { s_flush + (m * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
-                dst[0] = acc[b][0];
-                dst[1] = acc[b][1];
+            for (int b = 0; b < NBO; ++b) {
                 acc[b][0] = 0.0;
                 acc[b][1] = 0.0;
             }
-            named_bar_sync(kBarMma, kJacMmaWarps * 32);
-            for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
-                int i { 0 };
-                int rem { e };
-                while (rem >= NA - i) {
-                    rem -= NA - i;
-                    ++i;
-                }
-                const int j { i + rem };
-                const int blk { tri_index(NB, i >> 3, j >> 3) };
-                const int within { (i & 7) * 8 + (j & 7) };
-                double total { 0.0 };
 #pragma unroll
-                for (int w = 0; w < kJacMmaWarps; ++w) {
-                    total += s_flush[(w * NBT + blk) * 64 + within];
-                }
-                partials[static_cast<long long>(slot) * NT + e] = total;
+            for (int e = 0; e < kDiagPerWarp; ++e) {
+                dacc[e] = 0.0;
             }
-            named_bar_sync(kBarMma, kJacMmaWarps * 32);
-            ++slot;
-        } };
-        for (int t = t0; t < t1; ++t) {
-            const int buf { (t - t0) & 1 };
-            walk.advance_to(a, t);
-            if (walk.set != cur_set) {
-                if (cur_set >= 0) {
-                    flush();
+            // Off-diagonal blocks: the contraction warps summed in fixed order;
+            // diagonal entries: the 32 lanes of their one owner (shuffle tree)
+            const auto flush { [&]() {
+                static_for<0, NB>([&](auto BI) {
+                    static_for<BI + 1, NB>([&](auto BJ) {
+                        constexpr int o { off_block_index(NB, BI, BJ) };
+                        double* dst { s_flush + (m * NBT + tri_index(NB, BI, BJ)) * 64
+                                      + frag_row * 8 + 2 * frag_pt };
+                        dst[0] = acc[o][0];
+                        dst[1] = acc[o][1];
+                        acc[o][0] = 0.0;
+                        acc[o][1] = 0.0;
+                    });
+                });
+                const auto flush_diag { [&](auto M) {
+                    static_for<Diag::begin(M, kJacMmaWarps), Diag::begin(M + 1, kJacMmaWarps)>(
+                      [&](auto E) {
+                          constexpr int i { Diag::table.row[E] };
+                          constexpr int j { Diag::table.col[E] };
+                          constexpr int local { E - Diag::begin(M, kJacMmaWarps) };
+                          const double total { warp_sum(dacc[local]) };
+                          dacc[local] = 0.0;
+                          if (lane == 0) {
+                              s_flush[tri_index(NB, i >> 3, i >> 3) * 64 + (i & 7) * 8 + (j & 7)] = total;
+                          }
+                      });
+                } };
+                switch (m) {
+                case 0: flush_diag(std::integral_constant<int, 0> {}); break;
+                case 1: flush_diag(std::integral_constant<int, 1> {}); break;
+                case 2: flush_diag(std::integral_constant<int, 2> {}); break;
+                default: flush_diag(std::integral_constant<int, 3> {}); break;
                 }
-                cur_set = walk.set;
-            }
-            named_bar_sync(kBarFull + buf, kJacThreads);
-            const double* stage { s_stage + buf * Shape::stage };
-            const double* frag_src[NB];
+                named_bar_sync(kBarMma, kJacMmaWarps * 32);
+                for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
+                    int i { 0 };
+                    int rem { e };
+                    while (rem >= NA - i) {
+                        rem -= NA - i;
+                        ++i;
+                    }
+                    const int j { i + rem };
+                    const int blk { tri_index(NB, i >> 3, j >> 3) };
+                    const int within { (i & 7) * 8 + (j & 7) };
+                    double total { 0.0 };
+                    if ((i >> 3) == (j >> 3)) {
+                        total = s_flush[blk * 64 + within]; // written by its owner
+                    } else {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
-            }
-            if (last_is_padding) {
-                frag_src[NB - 1] = s_zero + frag_in_line;
-            }
-            // rows beyond the end of a partial tile are zero; whole 32-row
-            // halves beyond it are skipped
-            const int rows { walk.len(t) - 64 * m };
-            const int ksteps { rows >= 64 ? 16 : (rows > 32 ? 16 : (rows > 0 ? 8 : 0)) };
-#pragma unroll 4
-            for (int ks = 0; ks < ksteps; ++ks) {
-                double frag[NB];
+                        for (int w = 0; w < kJacMmaWarps; ++w) {
+                            total += s_flush[(w * NBT + blk) * 64 + within];
+                        }
+                    }
+                    partials[static_cast<long long>(slot) * NT + e] = total;
+                }
+                named_bar_sync(kBarMma, kJacMmaWarps * 32);
+                ++slot;
+            } };
+            // One tile: 8 passes of 32 points (DFMA) interleaved with the 16
+            // k-steps of 4 points (DMMA) of this warp's 64 rows
+            const auto tile { [&](auto M, const double* stage, const int len) {
+                const double* frag_src[NB];
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    frag[b] = frag_src[b][ks * 4];
+                    frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
                 }
+                if (last_is_padding) {
+                    frag_src[NB - 1] = s_zero + frag_in_line;
+                }
+                // rows beyond the end of a partial tile are zero; whole groups
+                // of 32 beyond it are skipped
+                const int rows { len - 64 * m };
+                const int ksteps { rows > 32 ? 16 : (rows > 0 ? 8 : 0) };
+                const int passes { (len + 31) >> 5 };
+                const double* sp { stage + lane };
+#pragma unroll 2
+                for (int q = 0; q < 8; ++q) {
+                    if (q < passes) {
+                        diag_fma_pass<NA, M, kJacMmaWarps, LDP>(sp + 32 * q, dacc);
+                    }
+                    if (2 * q < ksteps) {
 #pragma unroll
-                for (int bi = 0; bi < NB; ++bi) {
+                        for (int ks = 2 * q; ks < 2 * q + 2; ++ks) {
+                            double frag[NB];
 #pragma unroll
-                    for (int bj = bi; bj < NB; ++bj) {
-                        dmma_m8n8k4(acc[tri_index(NB, bi, bj)], frag[bi], frag[bj]);
+                            for (int b = 0; b < NB; ++b) {
+                                frag[b] = frag_src[b][ks * 4];
+                            }
+                            static_for<0, NB>([&](auto BI) {
+                                static_for<BI + 1, NB>([&](auto BJ) {
+                                    dmma_m8n8k4(acc[off_block_index(NB, BI, BJ)], frag[BI], frag[BJ]);
+                                });
+                            });
+                        }
                     }
                 }
+            } };
+            for (int t = t0; t < t1; ++t) {
+                const int buf { (t - t0) & 1 };
+                walk.advance_to(a, t);
+                if (walk.set != cur_set) {
+                    if (cur_set >= 0) {
+                        flush();
+                    }
+                    cur_set = walk.set;
+                }
+                named_bar_sync(kBarFull + buf, kJacThreads);
+                const double* stage { s_stage + buf * Shape::stage };
+                const int len { walk.len(t) };
+                switch (m) {
+                case 0: tile(std::integral_constant<int, 0> {}, stage, len); break;
+                case 1: tile(std::integral_constant<int, 1> {}, stage, len); break;
+                case 2: tile(std::integral_constant<int, 2> {}, stage, len); break;
+                default: tile(std::integral_constant<int, 3> {}, stage, len); break;
+                }
+                if (t + 2 < t1) {
+                    named_bar_arrive(kBarEmpty + buf, kJacThreads);
+                }
             }
-            if (t + 2 < t1) {
-                named_bar_arrive(kBarEmpty + buf, kJacThreads);
+            flush();
+        } else {
+            double acc[NBT][2];
+#pragma unroll
+            for (int b = 0; b < NBT; ++b) {
+                acc[b][0] = 0.0;
+                acc[b][1] = 0.0;
             }
+            // Sum the contraction warps in fixed order, one partial (packed triangle)
+            const auto flush { [&]() {
+#pragma unroll
+                for (int b = 0; b < NBT; ++b) {
+                    double* dst { s_flush + (m * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
+                    dst[0] = acc[b][0];
+                    dst[1] = acc[b][1];
+                    acc[b][0] = 0.0;
+                    acc[b][1] = 0.0;
+                }
+                named_bar_sync(kBarMma, kJacMmaWarps * 32);
+                for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
+                    int i { 0 };
+                    int rem { e };
+                    while (rem >= NA - i) {
+                        rem -= NA - i;
+                        ++i;
+                    }
+                    const int j { i + rem };
+                    const int blk { tri_index(NB, i >> 3, j >> 3) };
+                    const int within { (i & 7) * 8 + (j & 7) };
+                    double total { 0.0 };
+#pragma unroll
+                    for (int w = 0; w < kJacMmaWarps; ++w) {
+                        total += s_flush[(w * NBT + blk) * 64 + within];
+                    }
+                    partials[static_cast<long long>(slot) * NT + e] = total;
+                }
+                named_bar_sync(kBarMma, kJacMmaWarps * 32);
+                ++slot;
+            } };
+            for (int t = t0; t < t1; ++t) {
+                const int buf { (t - t0) & 1 };
+                walk.advance_to(a, t);
+                if (walk.set != cur_set) {
+                    if (cur_set >= 0) {
+                        flush();
+                    }
+                    cur_set = walk.set;
+                }
+                named_bar_sync(kBarFull + buf, kJacThreads);
+                const double* stage { s_stage + buf * Shape::stage };
+                const double* frag_src[NB];
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
+                }
+                if (last_is_padding) {
+                    frag_src[NB - 1] = s_zero + frag_in_line;
+                }
+                // rows beyond the end of a partial tile are zero; whole 32-row
+                // halves beyond it are skipped
+                const int rows { walk.len(t) - 64 * m };
+                const int ksteps { rows >= 64 ? 16 : (rows > 32 ? 16 : (rows > 0 ? 8 : 0)) };
+#pragma unroll 4
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    double frag[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        frag[b] = frag_src[b][ks * 4];
+                    }
+#pragma unroll
+                    for (int bi = 0; bi < NB; ++bi) {
+#pragma unroll
+                        for (int bj = bi; bj < NB; ++bj) {
+                            dmma_m8n8k4(acc[tri_index(NB, bi, bj)], frag[bi], frag[bj]);
+                        }
+                    }
+                }
+                if (t + 2 < t1) {
+                    named_bar_arrive(kBarEmpty + buf, kJacThreads);
+                }
+            }
+            flush();
         }
-        flush();
     }
 }
 
@@ -1133,10 +1382,13 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ double s_red[kThreads / 32];
     __shared__ Pre s_prep;
     const int tid { static_cast<int>(threadIdx.x) };
-    const int t0 { static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
-                                    / gridDim.x) };
-    const int t1 { static_cast<int>(static_cast<long long>(a.n_tiles)
-                                    * (blockIdx.x + 1) / gridDim.x) };
+    const bool tabled { a.cta_tile_begin != nullptr };
+    const int t0 { tabled ? a.cta_tile_begin[blockIdx.x]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
+                                             / gridDim.x) };
+    const int t1 { tabled ? a.cta_tile_begin[blockIdx.x + 1]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles)
+                                             * (blockIdx.x + 1) / gridDim.x) };
     int slot { slot_base[blockIdx.x] };
     int cur_set { -1 };
     double v[NP];
@@ -1157,7 +1409,11 @@ __global__ void __launch_bounds__(kThreads)
     } };
     TileWalker walk {};
     if (t0 < t1) {
-        walk.seek(a, t0);
+        if (tabled) {
+            walk.load(a, a.cta_first_set[blockIdx.x]);
+        } else {
+            walk.seek(a, t0);
+        }
     }
     for (int t = t0; t < t1; ++t) {
         walk.advance_to(a, t);

@@ -355,6 +355,13 @@ class LMsolver:
     def getInvJTJ(self):
         return self._array(_capi.INV_JTJ)
 
+    def getInvJTJDiagonal(self):
+        """diag((J^T J)^-1), one entry per Jacobian column: the parameter
+        variances up to chi2/dof.  Computed from the block-arrow factors, so
+        available for any number of data sets (the dense getInvJTJ() is
+        limited to n^2 <= 2^27 entries)."""
+        return self._array(_capi.INV_JTJ_DIAGONAL)
+
     def getDelta1(self):
         return self._array(_capi.DELTA1)
 

@@ -93,10 +93,14 @@ typedef enum gadfit_b200_array
     GADFIT_B200_LEFT_SIDE = 3, /* dense n x n, JTJ + lambda DTD */
     GADFIT_B200_RIGHT_SIDE = 4, /* n */
     GADFIT_B200_RESIDUALS = 5, /* N */
-    GADFIT_B200_INV_JTJ = 6,   /* dense n x n */
+    GADFIT_B200_INV_JTJ = 6,   /* dense n x n, assembled from the block-arrow inverse */
     GADFIT_B200_DELTA1 = 7,    /* n */
     GADFIT_B200_DELTA2 = 8,    /* n (zeros unless acceleration is on) */
-    GADFIT_B200_OMEGA = 9      /* N (acceleration only) */
+    GADFIT_B200_OMEGA = 9,     /* N (acceleration only) */
+    /* diagonal of (J^T J)^-1, n entries: the parameter variances (times
+     * chi2/dof).  From the block-arrow factors, so available for any n --
+     * the dense GADFIT_B200_INV_JTJ is limited to n^2 <= 2^27 entries */
+    GADFIT_B200_INV_JTJ_DIAGONAL = 10
 } gadfit_b200_array;
 
 /* One record per trial step: the reference prints exactly this at debug

@@ -292,6 +292,11 @@ public:
     [[nodiscard]] auto getRightSide() -> const std::vector<double>& { return array(GADFIT_B200_RIGHT_SIDE); }
     [[nodiscard]] auto getResiduals() -> const std::vector<double>& { return array(GADFIT_B200_RESIDUALS); }
     [[nodiscard]] auto getInvJTJ() -> const std::vector<double>& { return array(GADFIT_B200_INV_JTJ); }
+    // diag((J^T J)^-1) from the block-arrow factors: any n (getInvJTJ() is dense, n^2 <= 2^27)
+    [[nodiscard]] auto getInvJTJDiagonal() -> const std::vector<double>&
+    {
+        return array(GADFIT_B200_INV_JTJ_DIAGONAL);
+    }
     [[nodiscard]] auto chi2() -> double
     {
         double out { 0.0 };

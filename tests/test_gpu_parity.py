@@ -59,6 +59,36 @@ def test_access_functions(c1, golden):
     np.testing.assert_allclose(prod, np.eye(5), atol=1e-10)
 
 
+@pytest.mark.parametrize("name,kwargs", [
+    ("C3", dict(n_sets=300, n_points=200, iteration_limit=3)),   # n = 1202 columns
+    ("C5", dict(n_sets=60, n_points=64, iteration_limit=2)),     # 4 shared + 3 local
+    ("C2", dict(n_sets=3, n_points=5000, iteration_limit=3)),    # shared only
+])
+def test_block_arrow_inverse_of_jtj(name, kwargs, c1):
+    """getInvJTJ (lm_solver.cpp:578-585 inverts the dense matrix) from the
+    block-arrow factors, any n: times getJTJ it is the identity; its diagonal
+    getter agrees; for n <= 304 it equals the oracle's dense inverse."""
+    from gadfit_b200 import LMsolver, workloads as W
+    w = W.WORKLOADS[name](**kwargs)
+    s = LMsolver(w.model)
+    w.setup(s)
+    s.fit(w.lambda0)
+    n = int(round(np.sqrt(s.getJTJ().size)))
+    jtj = s.getJTJ().reshape(n, n)
+    inv = s.getInvJTJ().reshape(n, n)
+    scale = np.sqrt(np.diag(jtj))
+    # conditioning-independent check: D^-1 JTJ D^-1 times D inv D
+    prod = (jtj / scale[:, None] / scale[None, :]) @ (inv * scale[:, None] * scale[None, :])
+    np.testing.assert_allclose(prod, np.eye(n), atol=1e-7)
+    np.testing.assert_allclose(inv, inv.T, rtol=1e-9, atol=1e-30)
+    np.testing.assert_allclose(s.getInvJTJDiagonal(), np.diag(inv), rtol=1e-12)
+    if n <= 304:
+        o = backends.oracle_solver(1)(w.model)
+        w.setup(o)
+        o.fit(w.lambda0)
+        np.testing.assert_allclose(inv, o.getInvJTJ().reshape(n, n), rtol=1e-6, atol=1e-12 * np.abs(inv).max())
+
+
 def test_exceptions(c1):
     """c++/tests/lm_solver.cpp:278-365 -> status codes -> same exception names"""
     import gadfit_b200 as g
