@@ -99,7 +99,7 @@ CORE_SYMBOLS = [
 PRODUCT_ONLY_SYMBOLS = [
     "default_gadf_options", "set_gadf_options", "get_stop_reason", "set_log",
     "n_models", "model_info", "load_models", "n_launches", "jacobian_kernel_time",
-    "status_name", "set_device", "upload", "invalidate_data", "comm_unique_id", "set_comm",
+    "status_name", "set_device", "upload", "invalidate_data", "set_phase_timers", "comm_unique_id", "set_comm",
     "partition", "measure_fp64_peak", "microbench", "comm_stats",
 ]
 
@@ -159,6 +159,7 @@ class Api:
                 "set_device": ([vp, C.c_int], C.c_int),
                 "upload": ([vp], C.c_int),
                 "invalidate_data": ([vp], C.c_int),
+                "set_phase_timers": ([vp, C.c_int], C.c_int),
                 "comm_unique_id": ([vp], C.c_int),
                 "set_comm": ([vp, C.c_int, C.c_int, vp], C.c_int),
                 "partition": ([C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),

@@ -112,6 +112,17 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
     return _compile_and_link(_units(), OUT, force, verbose, extra, ["-ldl"])
 
 
+def build_variant(tag: str, extra: list[str]) -> str:
+    """A/B builds for kernel tuning: the same library compiled with extra
+    flags (-DGADFIT_...=...) as gadfit_b200/_variants/libgadfit_b200_<tag>.so;
+    select it at run time with GADFIT_B200_LIB=<path>."""
+    out_dir = os.path.join(HERE, "_variants")
+    os.makedirs(out_dir, exist_ok=True)
+    units = [(src, os.path.join(OBJ, f"{tag}_{os.path.basename(obj)}"), flags) for src, obj, flags in _units()]
+    return _compile_and_link(units, os.path.join(out_dir, f"libgadfit_b200_{tag}.so"), True, False, extra,
+                             ["-ldl"])
+
+
 def build_plugin(sources: list[str], out: str, force: bool = True, verbose: bool = False,
                  extra: list[str] | None = None) -> str:
     """A model plug-in (include/gadfit_b200/model_plugin.h) from user .cu files."""

@@ -115,13 +115,19 @@ struct PhaseTimer
         }
         return events[used++];
     }
+    // false: count the calls only (no events on the stream)
+    bool enabled { true };
     auto start(cudaStream_t stream) -> void
     {
-        GADFIT_CUDA_TRY(cudaEventRecord(next(), stream));
+        if (enabled) {
+            GADFIT_CUDA_TRY(cudaEventRecord(next(), stream));
+        }
     }
     auto stop(cudaStream_t stream) -> void
     {
-        GADFIT_CUDA_TRY(cudaEventRecord(next(), stream));
+        if (enabled) {
+            GADFIT_CUDA_TRY(cudaEventRecord(next(), stream));
+        }
         ++calls;
     }
     // Call after the stream has been synchronised

@@ -117,6 +117,7 @@ struct ModelOpsImpl final : ModelOps
     // true: the software-pipelined Jacobian sweep (every warp evaluates tile
     // t + 1 while it contracts tile t); false: the warp-specialised one
     bool pipelined_jacobian { false };
+    bool chi2_staged_fits { false };
 
     auto init_device() -> void override
     {
@@ -166,8 +167,22 @@ struct ModelOpsImpl final : ModelOps
         } else if (jac != nullptr && std::strcmp(jac, "ws") == 0) {
             pipelined_jacobian = false;
         }
+        if constexpr (Chi2Shape<Model>::staged) {
+            GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_chi2<Model, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(Chi2Shape<Model>::smem_bytes)));
+            GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_chi2<Model, true>,
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared));
+            int staged_occupancy { 0 };
+            GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+              &staged_occupancy, k_chi2<Model, true>, kThreads, Chi2Shape<Model>::smem_bytes));
+            chi2_staged_fits = staged_occupancy >= 1;
+        }
+        // (the grid is sized for the direct-load variant; the staged one has the
+        // same or a lower occupancy and then simply runs more than one wave)
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &occupancy[0], k_chi2<Model>, kThreads, 0));
+          &occupancy[0], k_chi2<Model, false>, kThreads, 0));
         if (pipelined_jacobian) {
             GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
               &occupancy[1], k_jacobian<Model, true, false>, kThreads, Shape::smem_bytes));
@@ -202,7 +217,14 @@ struct ModelOpsImpl final : ModelOps
               double* partials,
               const TrialFinish& fin) const -> void override
     {
-        k_chi2<Model><<<grid, kThreads, 0, st>>>(a, partials, fin);
+        if constexpr (Chi2Shape<Model>::staged) {
+            if (chi2_staged_fits && a.n_tiles >= static_cast<long long>(kChi2StagedMinTiles) * grid) {
+                k_chi2<Model, true><<<grid, kThreads, Chi2Shape<Model>::smem_bytes, st>>>(
+                  a, partials, fin);
+                return;
+            }
+        }
+        k_chi2<Model, false><<<grid, kThreads, 0, st>>>(a, partials, fin);
     }
     auto jacobian(const int grid,
                   cudaStream_t st,

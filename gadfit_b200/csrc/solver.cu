@@ -3005,6 +3005,16 @@ int gadfit_b200_invalidate_data(gadfit_b200_solver* solver)
     return guarded(solver, [&] { solver->data_uploaded = false; });
 }
 
+int gadfit_b200_set_phase_timers(gadfit_b200_solver* solver, const int on)
+{
+    return guarded(solver, [&] {
+        for (PhaseTimer* t : { &solver->t_jacobian, &solver->t_chi2, &solver->t_linalg,
+                               &solver->t_omega, &solver->t_jac_kernel }) {
+            t->enabled = on != 0;
+        }
+    });
+}
+
 int gadfit_b200_comm_unique_id(void* id_128_bytes)
 {
     if (id_128_bytes == nullptr) {

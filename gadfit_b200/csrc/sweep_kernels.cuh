@@ -127,6 +127,27 @@ struct Chi2Tuning<Model, std::void_t<decltype(Model::chi2_unroll)>>
     static constexpr int unroll { Model::chi2_unroll };
     static constexpr int min_blocks { Model::chi2_unroll >= 8 ? 2 : 4 };
 };
+// Unrolled sweeps can stage x, y, 1/sigma of the NEXT group of tiles in shared
+// memory (LDGSTS, two buffers of `unroll` tiles) while the current group is
+// evaluated: the DRAM latency no longer sits between a group's loads and its
+// arithmetic (r02b: 30 % of the stall samples of config 2 were long-scoreboard).
+// Measured (r02i): config 2 (845 tiles per CTA) 486 -> 435 us per sweep;
+// config 3 (54 tiles per CTA, a sweep of 27 us) 27 -> 33 us -- the exposed
+// first fetch and the 96 KiB of shared memory per CTA cost more than the
+// overlap gives.  Both variants are compiled; the launcher takes the staged
+// one from kChi2StagedMinTiles tiles per CTA.
+#ifndef GADFIT_CHI2_STAGED
+#define GADFIT_CHI2_STAGED 1
+#endif
+constexpr int kChi2StagedMinTiles { 128 };
+template <class Model>
+struct Chi2Shape
+{
+    static constexpr int unroll { Chi2Tuning<Model>::unroll };
+    static constexpr bool staged { unroll >= 4 && GADFIT_CHI2_STAGED != 0 };
+    static constexpr size_t group_doubles { static_cast<size_t>(unroll) * 3 * 256 };
+    static constexpr size_t smem_bytes { staged ? 2 * group_doubles * sizeof(double) : 0 };
+};
 
 struct SweepArgs
 {
@@ -247,6 +268,11 @@ __device__ __forceinline__ void cp_async_commit()
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// all but the most recent commit group have landed
+__device__ __forceinline__ void cp_async_wait_all_but_one()
+{
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
 }
 
 // Packed upper triangle, row major: (i, j), i <= j, of an NA x NA matrix
@@ -374,7 +400,7 @@ __device__ __forceinline__ void finish_trial_in_last_block(const TrialFinish& fi
 // function is NOT applied (lm_solver.cpp:521-524).  One partial per CTA.
 // `sig` holds 1 / sigma_i (inverted once, at upload: the division leaves the
 // sweeps).
-template <class Model>
+template <class Model, bool kStaged>
 __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
   k_chi2(const SweepArgs a, double* __restrict__ block_partials, const TrialFinish fin)
 {
@@ -423,57 +449,77 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
             walk.seek(a, t0);
         }
     }
-    while (t < t1) {
-        walk.advance_to(a, t);
-        if (walk.set != cur_set) {
-            __syncthreads();
-            if (tid < NP) {
-                s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
-            }
-            __syncthreads();
-            if constexpr (HasPrepare<Model, ValueCtx>) {
-                if (tid < 32) { // one warp, a table entry per lane (fit_function.h: tabulate)
-                    ValueCtx pc { s_par, a.status };
-                    pc.prep_lane = tid;
-                    pc.prep_lanes = 32;
-                    store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
-                }
-                __syncthreads();
-            }
-            cur_set = walk.set;
+    // parameters (and prepare()) of the data set the walker stands on
+    const auto enter_set { [&]() {
+        __syncthreads();
+        if (tid < NP) {
+            s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
         }
-        const ValueCtx ctx { s_par, a.status };
-        const long long base { walk.off(t) + tid };
-        // W consecutive tiles of one data set (contiguous in memory; only the
-        // last may be partial): the loads are issued together and the unrolled
-        // evaluations share every parameter-only subexpression (1/w, ...) and
-        // constant.  Groups of kChi2Unroll tiles, then 4, 2, 1 for what is
-        // left of the data set; a thread adds its terms in ascending tile
-        // order whatever the grouping, so the sum does not depend on it.
-        const int avail { min(t1, walk.tile_end) - t };
-        const auto group { [&](auto width) {
-            constexpr int W { decltype(width)::value };
-            const int last_len { walk.len(t + W - 1) };
-            if constexpr (W == 1) {
-                // threads past the end of the data set evaluate nothing
-                if (tid < last_len) {
-                    const double f { value_of(evaluate_prepared(Model {}, ctx, s_prep, a.x[base])) };
-                    const double diff { (a.y[base] - f) * a.inv_sig[base] };
-                    sum += diff * diff;
-                }
-                ++t;
-                return;
+        __syncthreads();
+        if constexpr (HasPrepare<Model, ValueCtx>) {
+            if (tid < 32) { // one warp, a table entry per lane (fit_function.h: tabulate)
+                ValueCtx pc { s_par, a.status };
+                pc.prep_lane = tid;
+                pc.prep_lanes = 32;
+                store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
             }
+            __syncthreads();
+        }
+        cur_set = walk.set;
+    } };
+    // W consecutive tiles of one data set (contiguous in memory; only the
+    // last may be partial): the unrolled evaluations share every
+    // parameter-only subexpression (1/w, ...) and constant.  Groups of
+    // kChi2Unroll tiles, then 4, 2, 1 for what is left of the data set; a
+    // thread adds its terms in ascending tile order whatever the grouping, so
+    // the sum does not depend on it.
+    const auto group_width { [&](const TileWalker& w, const int tile) -> int {
+        const int avail { min(t1, w.tile_end) - tile };
+        if (kChi2Unroll > 4 && avail >= kChi2Unroll) {
+            return kChi2Unroll;
+        }
+        if (kChi2Unroll >= 4 && avail >= 4) {
+            return 4;
+        }
+        if (kChi2Unroll >= 2 && avail >= 2) {
+            return 2;
+        }
+        return 1;
+    } };
+    if constexpr (kStaged) {
+        static_assert(Chi2Shape<Model>::staged);
+        extern __shared__ double s_chi2_stage[]; // [2][kChi2Unroll][3][kTile]
+        constexpr int kGroup { static_cast<int>(Chi2Shape<Model>::group_doubles) };
+        // every thread copies, and later reads back, only its own elements
+        const auto prefetch { [&](const TileWalker& w, const int tile, const int width, const int buf) {
+            const int last_len { w.len(tile + width - 1) };
+            const long long first { w.off(tile) + tid };
+            double* dst { s_chi2_stage + buf * kGroup + tid };
+#pragma unroll
+            for (int u = 0; u < kChi2Unroll; ++u) {
+                if (u < width && (u + 1 < width || tid < last_len)) {
+                    const long long i { first + u * kTile };
+                    cp_async_8(dst + (3 * u) * kTile, a.x + i);
+                    cp_async_8(dst + (3 * u + 1) * kTile, a.y + i);
+                    cp_async_8(dst + (3 * u + 2) * kTile, a.inv_sig + i);
+                }
+            }
+            cp_async_commit();
+        } };
+        const auto evaluate_group { [&](auto width, const int buf) {
+            constexpr int W { decltype(width)::value };
+            const ValueCtx ctx { s_par, a.status };
+            const int last_len { walk.len(t + W - 1) };
+            const double* src { s_chi2_stage + buf * kGroup + tid };
             double x[W];
             double y[W];
             double sg[W];
 #pragma unroll
             for (int u = 0; u < W; ++u) {
                 const bool in { u + 1 < W || tid < last_len };
-                const long long i { base + u * kTile };
-                x[u] = in ? a.x[i] : 0.0;
-                y[u] = in ? a.y[i] : 0.0;
-                sg[u] = in ? a.inv_sig[i] : 1.0;
+                x[u] = in ? src[(3 * u) * kTile] : 0.0;
+                y[u] = in ? src[(3 * u + 1) * kTile] : 0.0;
+                sg[u] = in ? src[(3 * u + 2) * kTile] : 1.0;
             }
 #pragma unroll
             for (int u = 0; u < W; ++u) {
@@ -483,16 +529,95 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
                     sum += diff * diff;
                 }
             }
-            t += W;
         } };
-        if (kChi2Unroll > 4 && avail >= kChi2Unroll) {
-            group(std::integral_constant<int, kChi2Unroll> {});
-        } else if (kChi2Unroll >= 4 && avail >= 4) {
-            group(std::integral_constant<int, 4> {});
-        } else if (kChi2Unroll >= 2 && avail >= 2) {
-            group(std::integral_constant<int, 2> {});
-        } else {
-            group(std::integral_constant<int, 1> {});
+        int width { 0 };
+        int buf { 0 };
+        if (t0 < t1) {
+            walk.advance_to(a, t0);
+            width = group_width(walk, t0);
+            prefetch(walk, t0, width, 0);
+        }
+        while (t < t1) {
+            walk.advance_to(a, t);
+            if (walk.set != cur_set) {
+                enter_set();
+            }
+            const int t_next { t + width };
+            int width_next { 0 };
+            if (t_next < t1) {
+                TileWalker next { walk };
+                next.advance_to(a, t_next);
+                width_next = group_width(next, t_next);
+                prefetch(next, t_next, width_next, buf ^ 1);
+                cp_async_wait_all_but_one();
+            } else {
+                cp_async_wait_all();
+            }
+            if (width == kChi2Unroll) {
+                evaluate_group(std::integral_constant<int, kChi2Unroll> {}, buf);
+            } else if (width == 4) {
+                evaluate_group(std::integral_constant<int, 4> {}, buf);
+            } else if (width == 2) {
+                evaluate_group(std::integral_constant<int, 2> {}, buf);
+            } else {
+                evaluate_group(std::integral_constant<int, 1> {}, buf);
+            }
+            t = t_next;
+            width = width_next;
+            buf ^= 1;
+        }
+    } else {
+        while (t < t1) {
+            walk.advance_to(a, t);
+            if (walk.set != cur_set) {
+                enter_set();
+            }
+            const ValueCtx ctx { s_par, a.status };
+            const long long base { walk.off(t) + tid };
+            const auto group { [&](auto width) {
+                constexpr int W { decltype(width)::value };
+                const int last_len { walk.len(t + W - 1) };
+                if constexpr (W == 1) {
+                    // threads past the end of the data set evaluate nothing
+                    if (tid < last_len) {
+                        const double f { value_of(evaluate_prepared(Model {}, ctx, s_prep, a.x[base])) };
+                        const double diff { (a.y[base] - f) * a.inv_sig[base] };
+                        sum += diff * diff;
+                    }
+                    ++t;
+                    return;
+                }
+                double x[W];
+                double y[W];
+                double sg[W];
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const bool in { u + 1 < W || tid < last_len };
+                    const long long i { base + u * kTile };
+                    x[u] = in ? a.x[i] : 0.0;
+                    y[u] = in ? a.y[i] : 0.0;
+                    sg[u] = in ? a.inv_sig[i] : 1.0;
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const double f { value_of(evaluate_prepared(Model {}, ctx, s_prep, x[u])) };
+                    const double diff { (y[u] - f) * sg[u] };
+                    if (u + 1 < W || tid < last_len) {
+                        sum += diff * diff;
+                    }
+                }
+                t += W;
+            } };
+            const int width { group_width(walk, t) };
+            if (width == 1) {
+                group(std::integral_constant<int, 1> {});
+            } else if (width == 2) {
+                group(std::integral_constant<int, 2> {});
+            } else if (width == 4) {
+                group(std::integral_constant<int, 4> {});
+            } else {
+                group(std::integral_constant<int, kChi2Unroll> {});
+            }
         }
     }
     const double total { block_sum(sum, s_red) };
@@ -864,88 +989,6 @@ constexpr int kJacMmaWarps { 4 };
 constexpr int kJacThreads { (kJacEvalWarps + kJacMmaWarps) * 32 };
 static_assert(kJacEvalWarps * 32 == kTile);
 
-// Diagonal 8 x 8 blocks of M_s need only their upper triangle: on the tensor
-// path 28 of their 64 products are the mirror image of the other 36 (and the
-// last block multiplies padding columns), 40 % of all DMMA work for 21
-// columns.  With two or more column blocks the diagonal blocks are therefore
-// accumulated entry by entry on the FP64 FMA pipe (same datapath, no waste)
-// and only the off-diagonal blocks stay on DMMA: 21 columns cost 3 x 64 + 87
-// = 279 FMA per point instead of 6 x 64 = 384.
-//
-// DiagEntries<NA>: the upper-triangle entries (i <= j) of all diagonal blocks
-// in block order, row major within a block.
-template <int NA>
-struct DiagEntries
-{
-    static constexpr int NB { (NA + 7) / 8 };
-    static constexpr int count { [] {
-        int n { 0 };
-        for (int b = 0; b < NB; ++b) {
-            const int w { NA - 8 * b < 8 ? NA - 8 * b : 8 };
-            n += w * (w + 1) / 2;
-        }
-        return n;
-    }() };
-    struct Table
-    {
-        signed char row[count > 0 ? count : 1];
-        signed char col[count > 0 ? count : 1];
-    };
-    static constexpr Table table { [] {
-        Table t {};
-        int e { 0 };
-        for (int b = 0; b < NB; ++b) {
-            const int w { NA - 8 * b < 8 ? NA - 8 * b : 8 };
-            for (int i = 0; i < w; ++i) {
-                for (int j = i; j < w; ++j) {
-                    t.row[e] = static_cast<signed char>(8 * b + i);
-                    t.col[e] = static_cast<signed char>(8 * b + j);
-                    ++e;
-                }
-            }
-        }
-        return t;
-    }() };
-    // contraction warp m of W owns the entries [begin(m), begin(m + 1))
-    static constexpr int begin(const int m, const int W) { return count * m / W; }
-    static constexpr int per_warp(const int W) { return (count + W - 1) / W; }
-    // does warp m read column c?
-    static constexpr bool reads(const int m, const int W, const int c)
-    {
-        for (int e = begin(m, W); e < begin(m + 1, W); ++e) {
-            if (table.row[e] == c || table.col[e] == c) {
-                return true;
-            }
-        }
-        return false;
-    }
-};
-
-// Off-diagonal block (bi < bj) -> 0 .. NB (NB - 1) / 2 - 1, row major
-__host__ __device__ constexpr int off_block_index(const int NB, const int bi, const int bj)
-{
-    return tri_index(NB, bi, bj) - (bi + 1);
-}
-
-// One pass of the diagonal entries of contraction warp M over 32 points: lane
-// l holds the row of point l (column-major staging line `sp` = stage + point)
-template <int NA, int M, int W, int LDP, int N>
-__device__ __forceinline__ void diag_fma_pass(const double* __restrict__ sp, double (&dacc)[N])
-{
-    using D = DiagEntries<NA>;
-    double col[NA];
-    static_for<0, NA>([&](auto C) {
-        if constexpr (D::reads(M, W, C)) {
-            col[C] = sp[C * LDP];
-        }
-    });
-    static_for<D::begin(M, W), D::begin(M + 1, W)>([&](auto E) {
-        constexpr int i { D::table.row[E] };
-        constexpr int j { D::table.col[E] };
-        dacc[E - D::begin(M, W)] = ::fma(col[i], col[j], dacc[E - D::begin(M, W)]);
-    });
-}
-
 template <class Model>
 struct JacobianWsShape
 {
@@ -1136,226 +1179,86 @@ __global__ void __launch_bounds__(kJacThreads, 2)
         const int frag_in_line { 64 * m + frag_pt };
         const bool last_is_padding { 8 * (NB - 1) + frag_row >= NA };
         int slot { slot_base[blockIdx.x] };
-        if constexpr (NB >= 2) {
-            // ---- hybrid: off-diagonal blocks on DMMA (this warp's 64 rows),
-            // diagonal entries on DFMA (this warp's share of the entries, all
-            // 256 rows of the tile, lane = point)
-            using Diag = DiagEntries<NA>;
-            constexpr int NBO { NB * (NB - 1) / 2 };
-            constexpr int kDiagPerWarp { Diag::per_warp(kJacMmaWarps) };
-            double acc[NBO][2];
-            double dacc[kDiagPerWarp];
+        double acc[NBT][2];
 #pragma unroll
-            for (int b = 0; b < NBO; ++b) {
-                acc[b][0] = 0.0;
-                acc[b][1] = 0.0;
-            }
-#pragma unroll
-            for (int e = 0; e < kDiagPerWarp; ++e) {
-                dacc[e] = 0.0;
-            }
-            // Off-diagonal blocks: the contraction warps summed in fixed order;
-            // diagonal entries: the 32 lanes of their one owner (shuffle tree)
-            const auto flush { [&]() {
-                static_for<0, NB>([&](auto BI) {
-                    static_for<BI + 1, NB>([&](auto BJ) {
-                        constexpr int o { off_block_index(NB, BI, BJ) };
-                        double* dst { s_flush + (m * NBT + tri_index(NB, BI, BJ)) * 64
-                                      + frag_row * 8 + 2 * frag_pt };
-                        dst[0] = acc[o][0];
-                        dst[1] = acc[o][1];
-                        acc[o][0] = 0.0;
-                        acc[o][1] = 0.0;
-                    });
-                });
-                const auto flush_diag { [&](auto M) {
-                    static_for<Diag::begin(M, kJacMmaWarps), Diag::begin(M + 1, kJacMmaWarps)>(
-                      [&](auto E) {
-                          constexpr int i { Diag::table.row[E] };
-                          constexpr int j { Diag::table.col[E] };
-                          constexpr int local { E - Diag::begin(M, kJacMmaWarps) };
-                          const double total { warp_sum(dacc[local]) };
-                          dacc[local] = 0.0;
-                          if (lane == 0) {
-                              s_flush[tri_index(NB, i >> 3, i >> 3) * 64 + (i & 7) * 8 + (j & 7)] = total;
-                          }
-                      });
-                } };
-                switch (m) {
-                case 0: flush_diag(std::integral_constant<int, 0> {}); break;
-                case 1: flush_diag(std::integral_constant<int, 1> {}); break;
-                case 2: flush_diag(std::integral_constant<int, 2> {}); break;
-                default: flush_diag(std::integral_constant<int, 3> {}); break;
-                }
-                named_bar_sync(kBarMma, kJacMmaWarps * 32);
-                for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
-                    int i { 0 };
-                    int rem { e };
-                    while (rem >= NA - i) {
-                        rem -= NA - i;
-                        ++i;
-                    }
-                    const int j { i + rem };
-                    const int blk { tri_index(NB, i >> 3, j >> 3) };
-                    const int within { (i & 7) * 8 + (j & 7) };
-                    double total { 0.0 };
-                    if ((i >> 3) == (j >> 3)) {
-                        total = s_flush[blk * 64 + within]; // written by its owner
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < kJacMmaWarps; ++w) {
-                            total += s_flush[(w * NBT + blk) * 64 + within];
-                        }
-                    }
-                    partials[static_cast<long long>(slot) * NT + e] = total;
-                }
-                named_bar_sync(kBarMma, kJacMmaWarps * 32);
-                ++slot;
-            } };
-            // One tile: 8 passes of 32 points (DFMA) interleaved with the 16
-            // k-steps of 4 points (DMMA) of this warp's 64 rows
-            const auto tile { [&](auto M, const double* stage, const int len) {
-                const double* frag_src[NB];
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
-                }
-                if (last_is_padding) {
-                    frag_src[NB - 1] = s_zero + frag_in_line;
-                }
-                // rows beyond the end of a partial tile are zero; whole groups
-                // of 32 beyond it are skipped
-                const int rows { len - 64 * m };
-                const int ksteps { rows > 32 ? 16 : (rows > 0 ? 8 : 0) };
-                const int passes { (len + 31) >> 5 };
-                const double* sp { stage + lane };
-#pragma unroll 2
-                for (int q = 0; q < 8; ++q) {
-                    if (q < passes) {
-                        diag_fma_pass<NA, M, kJacMmaWarps, LDP>(sp + 32 * q, dacc);
-                    }
-                    if (2 * q < ksteps) {
-#pragma unroll
-                        for (int ks = 2 * q; ks < 2 * q + 2; ++ks) {
-                            double frag[NB];
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) {
-                                frag[b] = frag_src[b][ks * 4];
-                            }
-                            static_for<0, NB>([&](auto BI) {
-                                static_for<BI + 1, NB>([&](auto BJ) {
-                                    dmma_m8n8k4(acc[off_block_index(NB, BI, BJ)], frag[BI], frag[BJ]);
-                                });
-                            });
-                        }
-                    }
-                }
-            } };
-            for (int t = t0; t < t1; ++t) {
-                const int buf { (t - t0) & 1 };
-                walk.advance_to(a, t);
-                if (walk.set != cur_set) {
-                    if (cur_set >= 0) {
-                        flush();
-                    }
-                    cur_set = walk.set;
-                }
-                named_bar_sync(kBarFull + buf, kJacThreads);
-                const double* stage { s_stage + buf * Shape::stage };
-                const int len { walk.len(t) };
-                switch (m) {
-                case 0: tile(std::integral_constant<int, 0> {}, stage, len); break;
-                case 1: tile(std::integral_constant<int, 1> {}, stage, len); break;
-                case 2: tile(std::integral_constant<int, 2> {}, stage, len); break;
-                default: tile(std::integral_constant<int, 3> {}, stage, len); break;
-                }
-                if (t + 2 < t1) {
-                    named_bar_arrive(kBarEmpty + buf, kJacThreads);
-                }
-            }
-            flush();
-        } else {
-            double acc[NBT][2];
+        for (int b = 0; b < NBT; ++b) {
+            acc[b][0] = 0.0;
+            acc[b][1] = 0.0;
+        }
+        // Sum the contraction warps in fixed order, one partial (packed triangle)
+        const auto flush { [&]() {
 #pragma unroll
             for (int b = 0; b < NBT; ++b) {
+                double* dst { s_flush + (m * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
+                dst[0] = acc[b][0];
+                dst[1] = acc[b][1];
                 acc[b][0] = 0.0;
                 acc[b][1] = 0.0;
             }
-            // Sum the contraction warps in fixed order, one partial (packed triangle)
-            const auto flush { [&]() {
+            named_bar_sync(kBarMma, kJacMmaWarps * 32);
+            for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
+                int i { 0 };
+                int rem { e };
+                while (rem >= NA - i) {
+                    rem -= NA - i;
+                    ++i;
+                }
+                const int j { i + rem };
+                const int blk { tri_index(NB, i >> 3, j >> 3) };
+                const int within { (i & 7) * 8 + (j & 7) };
+                double total { 0.0 };
 #pragma unroll
-                for (int b = 0; b < NBT; ++b) {
-                    double* dst { s_flush + (m * NBT + b) * 64 + frag_row * 8 + 2 * frag_pt };
-                    dst[0] = acc[b][0];
-                    dst[1] = acc[b][1];
-                    acc[b][0] = 0.0;
-                    acc[b][1] = 0.0;
+                for (int w = 0; w < kJacMmaWarps; ++w) {
+                    total += s_flush[(w * NBT + blk) * 64 + within];
                 }
-                named_bar_sync(kBarMma, kJacMmaWarps * 32);
-                for (int e = mtid; e < NT; e += kJacMmaWarps * 32) {
-                    int i { 0 };
-                    int rem { e };
-                    while (rem >= NA - i) {
-                        rem -= NA - i;
-                        ++i;
-                    }
-                    const int j { i + rem };
-                    const int blk { tri_index(NB, i >> 3, j >> 3) };
-                    const int within { (i & 7) * 8 + (j & 7) };
-                    double total { 0.0 };
+                partials[static_cast<long long>(slot) * NT + e] = total;
+            }
+            named_bar_sync(kBarMma, kJacMmaWarps * 32);
+            ++slot;
+        } };
+        for (int t = t0; t < t1; ++t) {
+            const int buf { (t - t0) & 1 };
+            walk.advance_to(a, t);
+            if (walk.set != cur_set) {
+                if (cur_set >= 0) {
+                    flush();
+                }
+                cur_set = walk.set;
+            }
+            named_bar_sync(kBarFull + buf, kJacThreads);
+            const double* stage { s_stage + buf * Shape::stage };
+            const double* frag_src[NB];
 #pragma unroll
-                    for (int w = 0; w < kJacMmaWarps; ++w) {
-                        total += s_flush[(w * NBT + blk) * 64 + within];
-                    }
-                    partials[static_cast<long long>(slot) * NT + e] = total;
-                }
-                named_bar_sync(kBarMma, kJacMmaWarps * 32);
-                ++slot;
-            } };
-            for (int t = t0; t < t1; ++t) {
-                const int buf { (t - t0) & 1 };
-                walk.advance_to(a, t);
-                if (walk.set != cur_set) {
-                    if (cur_set >= 0) {
-                        flush();
-                    }
-                    cur_set = walk.set;
-                }
-                named_bar_sync(kBarFull + buf, kJacThreads);
-                const double* stage { s_stage + buf * Shape::stage };
-                const double* frag_src[NB];
+            for (int b = 0; b < NB; ++b) {
+                frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
+            }
+            if (last_is_padding) {
+                frag_src[NB - 1] = s_zero + frag_in_line;
+            }
+            // rows beyond the end of a partial tile are zero; whole 32-row
+            // halves beyond it are skipped
+            const int rows { walk.len(t) - 64 * m };
+            const int ksteps { rows >= 64 ? 16 : (rows > 32 ? 16 : (rows > 0 ? 8 : 0)) };
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) {
+                double frag[NB];
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    frag_src[b] = stage + (8 * b + frag_row) * LDP + frag_in_line;
+                    frag[b] = frag_src[b][ks * 4];
                 }
-                if (last_is_padding) {
-                    frag_src[NB - 1] = s_zero + frag_in_line;
-                }
-                // rows beyond the end of a partial tile are zero; whole 32-row
-                // halves beyond it are skipped
-                const int rows { walk.len(t) - 64 * m };
-                const int ksteps { rows >= 64 ? 16 : (rows > 32 ? 16 : (rows > 0 ? 8 : 0)) };
-#pragma unroll 4
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    double frag[NB];
 #pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        frag[b] = frag_src[b][ks * 4];
+                for (int bi = 0; bi < NB; ++bi) {
+#pragma unroll
+                    for (int bj = bi; bj < NB; ++bj) {
+                        dmma_m8n8k4(acc[tri_index(NB, bi, bj)], frag[bi], frag[bj]);
                     }
-#pragma unroll
-                    for (int bi = 0; bi < NB; ++bi) {
-#pragma unroll
-                        for (int bj = bi; bj < NB; ++bj) {
-                            dmma_m8n8k4(acc[tri_index(NB, bi, bj)], frag[bi], frag[bj]);
-                        }
-                    }
-                }
-                if (t + 2 < t1) {
-                    named_bar_arrive(kBarEmpty + buf, kJacThreads);
                 }
             }
-            flush();
+            if (t + 2 < t1) {
+                named_bar_arrive(kBarEmpty + buf, kJacThreads);
+            }
         }
+        flush();
     }
 }
 

@@ -429,6 +429,12 @@ class LMsolver:
         arrays at every fit(), lm_solver.h:105-113.)"""
         self._check(self._api.invalidate_data(self._h))
 
+    def setPhaseTimers(self, on: bool):
+        """The per-phase CUDA-event timers (timings(), jacobianKernelTime()) are
+        on by default; off saves twelve event records per trial step, which
+        shows when a trial step takes ~100 us (gadfit_b200_set_phase_timers)."""
+        self._check(self._api.set_phase_timers(self._h, 1 if on else 0))
+
     def setComm(self, rank: int, world_size: int, unique_id: bytes):
         assert len(unique_id) == 128
         self._id_keep = C.create_string_buffer(unique_id, 128)

@@ -311,6 +311,14 @@ GADFIT_B200_API int gadfit_b200_upload(gadfit_b200_solver* solver);
  * x / y / errors in place, call this: the next fit() / chi2() / upload()
  * copies them again (the arrays must then be alive again until it has). */
 GADFIT_B200_API int gadfit_b200_invalidate_data(gadfit_b200_solver* solver);
+/* The five phase timers of the reference (lm_solver.h:140-144) are CUDA event
+ * pairs around each phase of every trial step.  They are on by default, as in
+ * the reference; in the latency-bound regime (a trial step of ~100 us) the
+ * twelve event records per trial are a measurable share of the step, so a
+ * caller that does not read gadfit_b200_get_timings / the Jacobian kernel
+ * time can switch them off (on != 0: on).  The whole-fit timer ("main")
+ * always runs. */
+GADFIT_B200_API int gadfit_b200_set_phase_timers(gadfit_b200_solver* solver, int on);
 
 /* One process per GPU.  Rank 0 obtains an id, the caller broadcasts the 128
  * bytes (torch.distributed / MPI / sockets) and every rank attaches.  All

@@ -218,6 +218,8 @@ public:
     // the next fit() copies them again.
     auto upload() -> void { check(gadfit_b200_upload(handle)); }
     auto invalidateData() -> void { check(gadfit_b200_invalidate_data(handle)); }
+    // per-phase event timers (default on, as the reference's Timers); off for latency-bound fits
+    auto setPhaseTimers(const bool on) -> void { check(gadfit_b200_set_phase_timers(handle, on ? 1 : 0)); }
 
     // lm_solver.h:158-167.  Arrays are borrowed, as in the reference.
     auto addDataset(const auto& x_data, const auto& y_data, const auto& errors) -> void
