@@ -784,6 +784,31 @@ struct SmallSolveArgs
     double* par;
     double* par_old;
     double* par_jac;
+    int in_smem;        // one pass (n_sets <= 1024) and the per-data-set records fit in shared memory
+};
+
+// Shared-memory residency of k_solve_small (in_smem): every CTA keeps M_s, the
+// local damping diagonal, both contribution rows and the local factors of ITS
+// 128 data sets in shared memory between the stages, so the dependent chain
+// slot sums -> prepare -> factorisation -> column sums -> back-substitution
+// runs on ~30-cycle shared-memory accesses instead of L2 round trips (r02j:
+// 44 us per solve on config 3 for 0.2 M warp instructions, 56 % of the stall
+// samples at the stage barriers, 30 % long scoreboard).  Global memory still
+// receives M and the damping diagonal (a rejected step re-solves from them
+// with a new lambda) -- written, not read back.
+template <int NP>
+struct SmallSolveSmem
+{
+    static constexpr int NA { NP + 1 };
+    static constexpr int NT { NA * (NA + 1) / 2 };
+    // doubles per CTA for VG contribution entries per data set
+    static constexpr size_t doubles(const int VG)
+    {
+        return static_cast<size_t>(kSmallSetThreads)
+               * (NT + NP + 2 * static_cast<size_t>(VG) + sizeof(LocalFactor<NP>) / sizeof(double));
+    }
+    static constexpr size_t bytes(const int VG) { return doubles(VG) * sizeof(double); }
+    static_assert(sizeof(LocalFactor<NP>) % sizeof(double) == 0);
 };
 
 // Stage 1 of k_column_sums for the chunks whose rows this CTA produced
@@ -839,7 +864,7 @@ __device__ __forceinline__ void cluster_barrier()
 // k_reduce_slots + k_local_prepare + column sums (first trial), k_local_schur
 // + column sums, k_shared_solve, k_local_backsolve, k_update_parameters
 template <int NP>
-__global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThreads)
+__global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThreads, 1)
   k_solve_small(const SmallSolveArgs a_in)
 {
     constexpr int NA { NP + 1 };
@@ -855,6 +880,7 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
         a.prepare = phase == kPhaseNewIteration ? 1 : 0;
     }
     __shared__ double s_L[kMaxShared][kMaxShared + 1];
+    extern __shared__ double s_small[];
     const int tid { static_cast<int>(threadIdx.x) };
     const int cta { static_cast<int>(blockIdx.x) }; // grid == one cluster
     const int g { cta * kSmallThreads + tid };
@@ -866,17 +892,52 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
     // the data set this thread owns in the first pass (threads >= 128: none)
     const int my_set { tid < kSmallSetThreads ? cta * kSmallSetThreads + tid : a.n_sets };
     LocalFactor<NP>* factors { static_cast<LocalFactor<NP>*>(a.factors) };
+    double* contrib_shared { a.contrib };
     double* contrib_schur { a.contrib + static_cast<long long>(a.n_sets) * a.VG };
     double* stage_schur { a.stage + static_cast<long long>(chunks) * a.VG };
+    // Where the stages read and write the per-data-set records: global memory,
+    // or (in_smem) this CTA's shared-memory copies, addressed by the global
+    // data-set index like the global arrays (base pointers shifted by set0)
+    const int set0 { cta * kSmallSetThreads };
+    const int n_own { max(0, min(kSmallSetThreads, a.n_sets - set0)) };
+    const double* M_in { a.M };
+    double* dtd { a.dtd_local };
+    if (a.in_smem != 0) {
+        double* s_M { s_small };
+        double* s_dtd { s_M + kSmallSetThreads * NT };
+        double* s_contrib { s_dtd + kSmallSetThreads * NP };
+        double* s_contrib2 { s_contrib + kSmallSetThreads * a.VG };
+        LocalFactor<NP>* s_F { reinterpret_cast<LocalFactor<NP>*>(s_contrib2 + kSmallSetThreads * a.VG) };
+        // local damping diagonal of the own data sets (read-modify-write below)
+        for (int i = tid; i < n_own * NP; i += kSmallThreads) {
+            s_dtd[i] = a.dtd_local[static_cast<long long>(set0) * NP + i];
+        }
+        if (a.prepare == 0) {
+            // a retry: M of the last Jacobian sweep
+            for (int i = tid; i < n_own * NT; i += kSmallThreads) {
+                s_M[i] = a.M[static_cast<long long>(set0) * NT + i];
+            }
+        }
+        M_in = s_M - static_cast<long long>(set0) * NT;
+        dtd = s_dtd - static_cast<long long>(set0) * NP;
+        contrib_shared = s_contrib - static_cast<long long>(set0) * a.VG;
+        contrib_schur = s_contrib2 - static_cast<long long>(set0) * a.VG;
+        factors = s_F - set0;
+    }
     if (a.prepare != 0) {
         for (int i = g; i < n_par; i += cluster_threads) {
             a.par_jac[i] = a.par[i];
         }
         // k_reduce_slots, four entries per thread at a time so that their
         // (dependent) index and partial loads overlap; each entry still adds
-        // its slots in ascending order
-        const int n_items { a.n_sets * NT };
-        for (int base = g; base < n_items; base += 4 * cluster_threads) {
+        // its slots in ascending order.  in_smem: every CTA reduces the slots
+        // of its own data sets (no cluster barrier before the next stage).
+        const int item0 { a.in_smem != 0 ? set0 * NT : 0 };
+        const int n_items { a.in_smem != 0 ? (set0 + n_own) * NT : a.n_sets * NT };
+        const int first_item { item0 + (a.in_smem != 0 ? tid : g) };
+        const int item_stride { a.in_smem != 0 ? kSmallThreads : cluster_threads };
+        double* M_out { const_cast<double*>(M_in) };
+        for (int base = first_item; base < n_items; base += 4 * item_stride) {
             int first[4];
             int count[4];
             int col[4];
@@ -884,7 +945,7 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
             int max_count { 0 };
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int idx { base + u * cluster_threads };
+                const int idx { base + u * item_stride };
                 const bool valid { idx < n_items };
                 const int s { valid ? idx / NT : 0 };
                 col[u] = idx - s * NT;
@@ -903,39 +964,75 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int idx { base + u * cluster_threads };
+                const int idx { base + u * item_stride };
                 if (idx < n_items) {
                     a.M[idx] = sum[u];
+                    if (a.in_smem != 0) {
+                        M_out[idx] = sum[u];
+                    }
                 }
             }
         }
-        cluster_barrier();
+        if (a.in_smem != 0) {
+            __syncthreads();
+        } else {
+            cluster_barrier();
+        }
         // k_local_prepare.  More than one chunk: 4 lanes per data set, inside
         // the CTA that owns it (which then sums the rows of its chunks);
         // a single chunk (all of it owned by CTA 0, no stage 1): 8 lanes per data set
         if (chunks > 1) {
             constexpr int lanes { kSmallThreads / kSmallSetThreads };
             for (int s = cta * kSmallSetThreads + tid / lanes; s < a.n_sets; s += sets_per_pass) {
-                local_prepare_set<NP>(s, tid % lanes, lanes, a.M, a.active, a.global_mask,
-                                      a.damp_max, a.dtd_local, a.contrib, a.VG);
+                local_prepare_set<NP>(s, tid % lanes, lanes, M_in, a.active, a.global_mask,
+                                      a.damp_max, dtd, contrib_shared, a.VG);
             }
         } else if (cta == 0) {
             constexpr int lanes { kSmallThreads / kColumnChunk };
             if (tid / lanes < a.n_sets) {
-                local_prepare_set<NP>(tid / lanes, tid % lanes, lanes, a.M, a.active,
-                                      a.global_mask, a.damp_max, a.dtd_local, a.contrib, a.VG);
+                local_prepare_set<NP>(tid / lanes, tid % lanes, lanes, M_in, a.active,
+                                      a.global_mask, a.damp_max, dtd, contrib_shared, a.VG);
             }
         }
         __syncthreads();
-        column_sums_own_chunks(cta, a.contrib, a.n_sets, a.VG, a.stage);
+        if (a.in_smem != 0) {
+            // the updated damping diagonal goes back to global memory (retries,
+            // the next iteration's max rule, getDTD)
+            for (int i = tid; i < n_own * NP; i += kSmallThreads) {
+                a.dtd_local[static_cast<long long>(set0) * NP + i] = dtd[static_cast<long long>(set0) * NP + i];
+            }
+            if (chunks == 1 && cta == 0) {
+                // column_sums_final reads the rows of a single chunk directly
+                for (int i = tid; i < n_own * a.VG; i += kSmallThreads) {
+                    a.contrib[i] = contrib_shared[i];
+                }
+            }
+        }
+        column_sums_own_chunks(cta, contrib_shared, a.n_sets, a.VG, a.stage);
+    } else if (a.in_smem != 0) {
+        __syncthreads(); // s_M, s_dtd of a retry are in place
     }
     const double lambda { a.state->lambda };
+    // (one pass: the current parameters of the own data set are fetched now,
+    // not after the second cluster barrier)
+    double p_now[NP];
+    if (a.in_smem != 0 && a.update != 0 && my_set < a.n_sets) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            p_now[k] = a.par[my_set * NP + k];
+        }
+    }
     if (a.has_locals != 0) {
         for (int s = my_set; s < a.n_sets; s += sets_per_pass) {
             local_schur_set<NP>(
-              s, a.M, a.active, a.global_mask, a.dtd_local, lambda, factors, contrib_schur, a.VG);
+              s, M_in, a.active, a.global_mask, dtd, lambda, factors, contrib_schur, a.VG);
         }
         __syncthreads();
+        if (a.in_smem != 0 && chunks == 1 && cta == 0) {
+            for (int i = tid; i < n_own * a.VG; i += kSmallThreads) {
+                a.contrib[static_cast<long long>(a.n_sets) * a.VG + i] = contrib_schur[i];
+            }
+        }
         column_sums_own_chunks(cta, contrib_schur, a.n_sets, a.VG, stage_schur);
     }
     cluster_barrier();
@@ -944,7 +1041,8 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
             column_sums_final(a.contrib, a.stage, a.n_sets, a.VG, a.shared_sums);
         }
         if (a.has_locals != 0) {
-            column_sums_final(contrib_schur, stage_schur, a.n_sets, a.VG, a.schur_sums);
+            column_sums_final(a.contrib + static_cast<long long>(a.n_sets) * a.VG, stage_schur,
+                              a.n_sets, a.VG, a.schur_sums);
         }
         __syncthreads();
         if (tid < 32 && a.pg > 0) {
@@ -961,7 +1059,7 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
                 const int i { s * NP + k };
-                const double p { a.par[i] };
+                const double p { a.in_smem != 0 ? p_now[k] : a.par[i] };
                 if (a.prepare != 0) {
                     a.par_old[i] = p;
                 }

@@ -118,6 +118,8 @@ struct ModelOpsImpl final : ModelOps
     // t + 1 while it contracts tile t); false: the warp-specialised one
     bool pipelined_jacobian { false };
     bool chi2_staged_fits { false };
+    bool small_smem_ready { false };
+    static constexpr size_t kSmallSmemLimit { 200 * 1024 };
 
     auto init_device() -> void override
     {
@@ -195,6 +197,13 @@ struct ModelOpsImpl final : ModelOps
           &occupancy[2], k_omega<Model>, kThreads, 0));
         for (int& o : occupancy) {
             o = o < 1 ? 1 : o;
+        }
+        small_smem_ready =
+          cudaFuncSetAttribute(k_solve_small<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(kSmallSmemLimit))
+          == cudaSuccess;
+        if (!small_smem_ready) {
+            cudaGetLastError(); // not fatal: the global-memory stages are used
         }
         device_ready = true;
     }
@@ -371,7 +380,14 @@ struct ModelOpsImpl final : ModelOps
     }
     auto solve_small(cudaStream_t st, const SmallSolveArgs& a) const -> void override
     {
-        k_solve_small<NP><<<kSmallCtas, kSmallThreads, 0, st>>>(a); // one cluster
+        // shared-memory residency: one pass of the cluster and the records fit
+        SmallSolveArgs b { a };
+        const size_t bytes { SmallSolveSmem<NP>::bytes(a.VG) };
+        b.in_smem = (small_smem_ready && a.n_sets <= kSmallCtas * kSmallSetThreads
+                     && bytes <= kSmallSmemLimit)
+                      ? 1
+                      : 0;
+        k_solve_small<NP><<<kSmallCtas, kSmallThreads, b.in_smem != 0 ? bytes : 0, st>>>(b); // one cluster
     }
 };
 

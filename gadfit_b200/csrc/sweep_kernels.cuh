@@ -674,6 +674,24 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], const double a, cons
 // If J_out != nullptr the weighted Jacobian rows are stored parameter-major
 // (J_out[k * n_points + i]) for the omega sweep and getJacobian(); if
 // r_out != nullptr so are the weighted residuals (kStore instantiation only).
+// Resident CTAs per SM the software-pipelined Jacobian sweep is compiled for
+// (register cap 65536 / (256 * blocks)).  Default 2 (128 registers: the
+// quadrature models want them); a cheap closed-form function may state
+// `static constexpr int jacobian_blocks` -- with ~100 FP64 instructions per
+// point the sweep is latency bound and more resident warps pay.
+template <class Model, class = void>
+struct JacobianTuning
+{
+    static constexpr int min_blocks { 2 };
+};
+#ifndef GADFIT_NO_JACOBIAN_HINT
+template <class Model>
+struct JacobianTuning<Model, std::void_t<decltype(Model::jacobian_blocks)>>
+{
+    static constexpr int min_blocks { Model::jacobian_blocks };
+};
+#endif
+
 template <class Model>
 struct JacobianShape
 {
@@ -707,7 +725,7 @@ struct JacobianShape
 };
 
 template <class Model, bool kStore, bool kLinearLoss>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, JacobianTuning<Model>::min_blocks)
   k_jacobian(const SweepArgs a,
              const int loss_type,
              const int* __restrict__ slot_base,
@@ -797,7 +815,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     // x, y, 1/sigma of the tile after next are copied asynchronously (LDGSTS)
     // into a double-buffered staging area: the DRAM latency hides behind a
     // whole tile of work without holding registers.  Every thread reads back
-    // only what it requested itself.
+    // only what it requested itself.  (A ring of three slots -- two tiles in
+    // flight -- was measured, r02k: config 3 57.6 vs 56.7 us per sweep, config 5
+    // 8.91 vs 8.67 ms; the walker look-ahead costs what the deeper queue gives.)
     // Threads past the end of a data set's last tile fetch its last point: in
     // the pipelined block they evaluate a VALID point (an adaptive integral
     // over a degenerate dummy range would never converge) and zero their row.

@@ -368,8 +368,7 @@ def test_fused_small_problem_path_is_bit_identical_to_the_stagewise_path(sc, c1,
     if sc["name"] != "no_iteration_limit":
         # (without an iteration limit the device-driven loop pre-enqueues a batch
         # of trial slots; those past the end of the fit skip themselves but count)
-        assert fs.launches() <= ss.launches()
-    assert fused["iterations"] == 0 or fs.launches() < ss.launches()
+        assert fused["iterations"] == 0 or fs.launches() < ss.launches()
     for getter in ("getJTJ", "getDTD", "getRightSide", "getLeftSide"):
         if fused["dof"] < 10_000:  # dense getters: small cases only
             np.testing.assert_array_equal(getattr(fs, getter)(), getattr(ss, getter)())
