@@ -26,6 +26,9 @@
 #pragma once
 
 #include "sweep_kernels.cuh"
+#ifdef GADFIT_SOLVE_SMALL_TIMING
+#include <cstdio>
+#endif
 
 namespace gadfit_b200 {
 
@@ -223,7 +226,7 @@ __global__ void k_local_prepare(const double* __restrict__ M,
 // Per trial step: factorise the damped local block and emit the Schur
 // contribution [Y'Y (pg x pg packed upper), Y'z (pg)].  The Cholesky loop
 // order is that of the reference's in-tree dpptrf (lapack_fallback.cpp:59-81).
-template <int NP>
+template <int NP, bool kBurst = true>
 __device__ __forceinline__ void local_schur_into(LocalFactor<NP>& F,
                                                  const int s,
                                                  const double* __restrict__ M,
@@ -239,8 +242,8 @@ __device__ __forceinline__ void local_schur_into(LocalFactor<NP>& F,
     const double* Ms { M + static_cast<long long>(s) * NT };
     // (small NP: all of M_s in one burst of loads instead of on demand inside
     // the dependent chains below)
-    double m_local[NP <= 8 ? NT : 1];
-    if constexpr (NP <= 8) {
+    double m_local[NP <= 8 && kBurst ? NT : 1];
+    if constexpr (NP <= 8 && kBurst) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             m_local[t] = Ms[t];
@@ -329,8 +332,16 @@ __device__ __forceinline__ void local_schur_set(const int s,
                                                 const double lambda,
                                                 LocalFactor<NP>* __restrict__ factors,
                                                 double* __restrict__ contrib,
-                                                const int VG)
+                                                const int VG,
+                                                const bool in_shared = false)
 {
+    if (in_shared) {
+        // M_s and the factor live in shared memory: the chain of dependent
+        // read-modify-writes runs there directly (no burst copies)
+        local_schur_into<NP, false>(
+          factors[s], s, M, active, global_mask, dtd_local, lambda, contrib, VG);
+        return;
+    }
     if constexpr (NP <= 8) {
         LocalFactor<NP> F;
         local_schur_into<NP>(F, s, M, active, global_mask, dtd_local, lambda, contrib, VG);
@@ -584,8 +595,13 @@ __device__ __forceinline__ void local_backsolve_set(const int s,
                                                     const unsigned global_mask,
                                                     const LocalFactor<NP>* __restrict__ factors,
                                                     const double* __restrict__ delta_g,
-                                                    double* __restrict__ delta_par)
+                                                    double* __restrict__ delta_par,
+                                                    const bool in_shared = false)
 {
+    if (in_shared) {
+        local_backsolve_with<NP>(factors[s], s, active, global_mask, delta_g, delta_par);
+        return;
+    }
     if constexpr (NP <= 8) {
         const LocalFactor<NP> F { factors[s] }; // one burst of independent loads
         local_backsolve_with<NP>(F, s, active, global_mask, delta_g, delta_par);
@@ -839,19 +855,41 @@ __device__ __forceinline__ void column_sums_own_chunks(const int cta,
 }
 
 // Stage 2 of k_column_sums by one CTA
+// (by the threads [first, first + count) of the CTA; the result also goes to
+// shared memory, where the shared solve reads it without an L2 round trip)
 __device__ __forceinline__ void column_sums_final(const double* in,
                                                   const double* stage,
                                                   const int n_rows,
                                                   const int V,
-                                                  double* out)
+                                                  double* out,
+                                                  double* out_shared,
+                                                  const int first,
+                                                  const int count)
 {
     const int blocks { (n_rows + kColumnChunk - 1) / kColumnChunk };
     const double* last_in { blocks > 1 ? stage : in };
     const int last_rows { blocks > 1 ? blocks : n_rows };
-    for (int v = static_cast<int>(threadIdx.x); v < V; v += kSmallThreads) {
-        out[v] = ordered_column_sum(last_in, 0, last_rows, V, v);
+    const int t { static_cast<int>(threadIdx.x) - first };
+    if (t < 0 || t >= count) {
+        return;
+    }
+    for (int v = t; v < V; v += count) {
+        const double sum { ordered_column_sum(last_in, 0, last_rows, V, v) };
+        out[v] = sum;
+        out_shared[v] = sum;
     }
 }
+
+#ifdef GADFIT_SOLVE_SMALL_TIMING
+// Developer build (gadfit_b200.build.build_variant): wall-clock stamps of the
+// stages of k_solve_small, printed by thread 0 of CTA 0
+#define GADFIT_STAMP(k)                                                                   \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                            \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamp[k]));                      \
+    }
+#else
+#define GADFIT_STAMP(k)
+#endif
 
 __device__ __forceinline__ void cluster_barrier()
 {
@@ -880,7 +918,13 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
         a.prepare = phase == kPhaseNewIteration ? 1 : 0;
     }
     __shared__ double s_L[kMaxShared][kMaxShared + 1];
+    constexpr int kMaxVG { kMaxShared * (kMaxShared + 1) / 2 + kMaxShared };
+    __shared__ double s_sums[2 * kMaxVG]; // [G, b_g] and the Schur sums, as the shared solve reads them
     extern __shared__ double s_small[];
+#ifdef GADFIT_SOLVE_SMALL_TIMING
+    unsigned long long stamp[10] {};
+#endif
+    GADFIT_STAMP(0)
     const int tid { static_cast<int>(threadIdx.x) };
     const int cta { static_cast<int>(blockIdx.x) }; // grid == one cluster
     const int g { cta * kSmallThreads + tid };
@@ -925,9 +969,6 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
         factors = s_F - set0;
     }
     if (a.prepare != 0) {
-        for (int i = g; i < n_par; i += cluster_threads) {
-            a.par_jac[i] = a.par[i];
-        }
         // k_reduce_slots, four entries per thread at a time so that their
         // (dependent) index and partial loads overlap; each entry still adds
         // its slots in ascending order.  in_smem: every CTA reduces the slots
@@ -954,11 +995,27 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
                 max_count = max(max_count, count[u]);
                 sum[u] = 0.0;
             }
-            for (int c = 0; c < max_count; ++c) {
+            // (two slots per step: the loads of slot c + 1 do not wait for the
+            // addition of slot c; the additions stay in ascending slot order)
+            for (int c = 0; c < max_count; c += 2) {
+                double p0[4];
+                double p1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    p0[u] = c < count[u]
+                              ? a.jac_partials[static_cast<long long>(first[u] + c) * NT + col[u]]
+                              : 0.0;
+                    p1[u] = c + 1 < count[u]
+                              ? a.jac_partials[static_cast<long long>(first[u] + c + 1) * NT + col[u]]
+                              : 0.0;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (c < count[u]) {
-                        sum[u] += a.jac_partials[static_cast<long long>(first[u] + c) * NT + col[u]];
+                        sum[u] += p0[u];
+                    }
+                    if (c + 1 < count[u]) {
+                        sum[u] += p1[u];
                     }
                 }
             }
@@ -978,6 +1035,7 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
         } else {
             cluster_barrier();
         }
+        GADFIT_STAMP(1)
         // k_local_prepare.  More than one chunk: 4 lanes per data set, inside
         // the CTA that owns it (which then sums the rows of its chunks);
         // a single chunk (all of it owned by CTA 0, no stage 1): 8 lanes per data set
@@ -1008,9 +1066,19 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
                 }
             }
         }
+        GADFIT_STAMP(2)
         column_sums_own_chunks(cta, contrib_shared, a.n_sets, a.VG, a.stage);
+        GADFIT_STAMP(3)
     } else if (a.in_smem != 0) {
         __syncthreads(); // s_M, s_dtd of a retry are in place
+    }
+    if (a.prepare != 0 && tid >= kSmallSetThreads) {
+        // the parameters of this Jacobian, copied by the threads that own no
+        // data set (they idle through the factorisation below)
+        constexpr int idle { kSmallThreads - kSmallSetThreads };
+        for (int i = cta * idle + (tid - kSmallSetThreads); i < n_par; i += kSmallCtas * idle) {
+            a.par_jac[i] = a.par[i];
+        }
     }
     const double lambda { a.state->lambda };
     // (one pass: the current parameters of the own data set are fetched now,
@@ -1024,10 +1092,11 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
     }
     if (a.has_locals != 0) {
         for (int s = my_set; s < a.n_sets; s += sets_per_pass) {
-            local_schur_set<NP>(
-              s, M_in, a.active, a.global_mask, dtd, lambda, factors, contrib_schur, a.VG);
+            local_schur_set<NP>(s, M_in, a.active, a.global_mask, dtd, lambda, factors,
+                                contrib_schur, a.VG, a.in_smem != 0);
         }
         __syncthreads();
+        GADFIT_STAMP(4)
         if (a.in_smem != 0 && chunks == 1 && cta == 0) {
             for (int i = tid; i < n_own * a.VG; i += kSmallThreads) {
                 a.contrib[static_cast<long long>(a.n_sets) * a.VG + i] = contrib_schur[i];
@@ -1035,24 +1104,40 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
         }
         column_sums_own_chunks(cta, contrib_schur, a.n_sets, a.VG, stage_schur);
     }
+    GADFIT_STAMP(5)
     cluster_barrier();
+    GADFIT_STAMP(6)
     if (cta == 0) {
+        // The two sums by different halves of the CTA (their loads overlap),
+        // kept in shared memory for the solve as well
+        constexpr int half { kSmallThreads / 2 };
         if (a.prepare != 0) {
-            column_sums_final(a.contrib, a.stage, a.n_sets, a.VG, a.shared_sums);
+            column_sums_final(a.contrib, a.stage, a.n_sets, a.VG, a.shared_sums, s_sums, 0, half);
+        } else if (tid < half) {
+            for (int v = tid; v < a.VG; v += half) {
+                s_sums[v] = a.shared_sums[v]; // a retry: the sums of this iteration
+            }
         }
         if (a.has_locals != 0) {
             column_sums_final(a.contrib + static_cast<long long>(a.n_sets) * a.VG, stage_schur,
-                              a.n_sets, a.VG, a.schur_sums);
+                              a.n_sets, a.VG, a.schur_sums, s_sums + kMaxVG, half, half);
+        } else if (tid >= half) {
+            for (int v = tid - half; v < a.VG; v += half) {
+                s_sums[kMaxVG + v] = a.schur_sums[v]; // zeros
+            }
         }
         __syncthreads();
         if (tid < 32 && a.pg > 0) {
-            shared_solve_warp(a.pg, 1, a.prepare, a.damp_max, a.shared_sums, a.schur_sums, nullptr,
+            shared_solve_warp(a.pg, 1, a.prepare, a.damp_max, s_sums, s_sums + kMaxVG, nullptr,
                               lambda, a.dtd_global, a.chol, a.delta_g, s_L);
         }
     }
+    GADFIT_STAMP(7)
     cluster_barrier();
+    GADFIT_STAMP(8)
     for (int s = my_set; s < a.n_sets; s += sets_per_pass) {
-        local_backsolve_set<NP>(s, a.active, a.global_mask, factors, a.delta_g, a.delta_par);
+        local_backsolve_set<NP>(s, a.active, a.global_mask, factors, a.delta_g, a.delta_par,
+                                a.in_smem != 0);
         if (a.update != 0) {
             // saveParameters (first trial) + updateParameters,
             // lm_solver.cpp:192-204,230-253
@@ -1067,6 +1152,16 @@ __global__ void __cluster_dims__(kSmallCtas, 1, 1) __launch_bounds__(kSmallThrea
             }
         }
     }
+#ifdef GADFIT_SOLVE_SMALL_TIMING
+    GADFIT_STAMP(9)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        printf("solve_small stages (ns): slots %llu prepare %llu sums1 %llu schur %llu sums2 %llu "
+               "barrier %llu shared_solve %llu barrier %llu backsolve %llu total %llu\n",
+               stamp[1] - stamp[0], stamp[2] - stamp[1], stamp[3] - stamp[2], stamp[4] - stamp[3],
+               stamp[5] - stamp[4], stamp[6] - stamp[5], stamp[7] - stamp[6], stamp[8] - stamp[7],
+               stamp[9] - stamp[8], stamp[9] - stamp[0]);
+    }
+#endif
 }
 
 // k_sum_partials + k_decide + k_revert_if_rejected

@@ -85,11 +85,7 @@ struct GaussLinearBg
 {
     static constexpr int n_pars { 6 };
     static constexpr const char* name { "gauss_linear_bg" };
-#ifdef GADFIT_AB_C3_CHI2_UNROLL
-    static constexpr int chi2_unroll { GADFIT_AB_C3_CHI2_UNROLL };
-#else
     static constexpr int chi2_unroll { 8 };
-#endif
     static constexpr int jacobian_blocks { 4 }; // tuning hint, see csrc/sweep_kernels.cuh
     template <class Ctx>
     GADFIT_HD auto prepare(const Ctx& c) const
