@@ -106,6 +106,7 @@ inline auto blocks_for(const long long n, const int threads) -> int
     return static_cast<int>((n + threads - 1) / threads);
 }
 
+
 template <class Model>
 struct ModelOpsImpl final : ModelOps
 {
@@ -117,6 +118,11 @@ struct ModelOpsImpl final : ModelOps
     // true: the software-pipelined Jacobian sweep (every warp evaluates tile
     // t + 1 while it contracts tile t); false: the warp-specialised one
     bool pipelined_jacobian { false };
+    // the register-accumulating sweep (cheap functions with few parameters)
+    bool register_jacobian { false };
+    // instantiated only for the functions that ask for it (hint
+    // `jacobian_in_registers`): four more kernels per function otherwise
+    static constexpr bool kHasRegisterJacobian { JacobianInRegisters<Model>::value };
     bool chi2_staged_fits { false };
     bool small_smem_ready { false };
     static constexpr size_t kSmallSmemLimit { 200 * 1024 };
@@ -155,6 +161,17 @@ struct ModelOpsImpl final : ModelOps
         configure_ws(k_jacobian_ws<Model, false, true>);
         configure_ws(k_jacobian_ws<Model, true, false>);
         configure_ws(k_jacobian_ws<Model, true, true>);
+        if constexpr (kHasRegisterJacobian) {
+            const auto configure_reg { [](auto* kernel) {
+                GADFIT_CUDA_TRY(cudaFuncSetAttribute(
+                  kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                  static_cast<int>(JacobianRegShape<Model>::smem_bytes)));
+            } };
+            configure_reg(k_jacobian_reg<Model, false, false>);
+            configure_reg(k_jacobian_reg<Model, false, true>);
+            configure_reg(k_jacobian_reg<Model, true, false>);
+            configure_reg(k_jacobian_reg<Model, true, true>);
+        }
         // Which Jacobian sweep (sweep_kernels.cuh).  Measured on B200 (r02c):
         // with several 8-column blocks the contraction dominates and dedicated
         // contraction warps win (config 2, 21 columns: 2.52 vs 2.62 ms); with a
@@ -164,10 +181,15 @@ struct ModelOpsImpl final : ModelOps
         // overrides the choice (A/B runs).
         const char* jac { std::getenv("GADFIT_B200_JAC") };
         pipelined_jacobian = Shape::NB < 2;
+        register_jacobian = JacobianInRegisters<Model>::value;
         if (jac != nullptr && std::strcmp(jac, "sp") == 0) {
             pipelined_jacobian = true;
+            register_jacobian = false;
         } else if (jac != nullptr && std::strcmp(jac, "ws") == 0) {
             pipelined_jacobian = false;
+            register_jacobian = false;
+        } else if (jac != nullptr && std::strcmp(jac, "reg") == 0) {
+            register_jacobian = kHasRegisterJacobian;
         }
         if constexpr (Chi2Shape<Model>::staged) {
             GADFIT_CUDA_TRY(cudaFuncSetAttribute(k_chi2<Model, true>,
@@ -185,7 +207,13 @@ struct ModelOpsImpl final : ModelOps
         // same or a lower occupancy and then simply runs more than one wave)
         GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
           &occupancy[0], k_chi2<Model, false>, kThreads, 0));
-        if (pipelined_jacobian) {
+        if (register_jacobian) {
+            if constexpr (kHasRegisterJacobian) {
+                GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                  &occupancy[1], k_jacobian_reg<Model, true, false>, kThreads,
+                  JacobianRegShape<Model>::smem_bytes));
+            }
+        } else if (pipelined_jacobian) {
             GADFIT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
               &occupancy[1], k_jacobian<Model, true, false>, kThreads, Shape::smem_bytes));
         } else {
@@ -247,6 +275,22 @@ struct ModelOpsImpl final : ModelOps
     {
         const bool store { J_out != nullptr || r_out != nullptr };
         const bool linear { loss == GADFIT_B200_LOSS_LINEAR };
+        if constexpr (kHasRegisterJacobian) {
+            if (register_jacobian) {
+                const auto launch { [&](auto* kernel) {
+                    kernel<<<grid, kThreads, JacobianRegShape<Model>::smem_bytes, st>>>(
+                      a, loss, slot_base, partials, J_out, r_out, n_points);
+                } };
+                if (store) {
+                    linear ? launch(k_jacobian_reg<Model, true, true>)
+                           : launch(k_jacobian_reg<Model, true, false>);
+                } else {
+                    linear ? launch(k_jacobian_reg<Model, false, true>)
+                           : launch(k_jacobian_reg<Model, false, false>);
+                }
+                return;
+            }
+        }
         if (!pipelined_jacobian) {
             const auto launch { [&](auto* kernel) {
                 kernel<<<grid, kJacThreads, WsShape::smem_bytes, st>>>(

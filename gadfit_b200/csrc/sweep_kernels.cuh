@@ -977,6 +977,232 @@ __global__ void __launch_bounds__(kThreads, JacobianTuning<Model>::min_blocks)
     }
 }
 
+// --------------------------------- Jacobian, accumulated in registers
+//
+// For a function with few parameters and a cheap closed form (BASELINE config
+// 3: 6 parameters, ~50 FP64 instructions per point) the 8 x 8 tensor tile is
+// mostly waste -- NA = 7 columns need 28 products per point, one DMMA block
+// computes 64, and the FP64 datapath then spends more cycles on the
+// contraction (8 DMMA x 16 cycles per 32 points) than on the evaluation.  A
+// thread already holds the augmented row of its point in registers: this
+// kernel keeps the NT = NA (NA + 1) / 2 entries of M_s as per-lane
+// accumulators and adds a_i a_j with one DFMA each, straight from the row --
+// no staging buffers, no shared-memory traffic, no barrier in the steady
+// state.  The lanes are summed by a shuffle tree and the warps in fixed order
+// when the data set changes (deterministic).  Chosen by the model hint
+// `static constexpr bool jacobian_in_registers` (the accumulators cost 2 NT
+// registers: 56 for NA = 7).
+template <class Model>
+struct JacobianRegShape
+{
+    static constexpr int NP { Model::n_pars };
+    static constexpr int NA { NP + 1 };
+    static constexpr int NT { NA * (NA + 1) / 2 };
+    static constexpr int kWarps { kThreads / 32 };
+    // tiles per group (one batch of copies / one pass of the bookkeeping)
+    static constexpr int kGroup { 4 };
+    static constexpr size_t smem_bytes { 2 * kGroup * 3 * kTile * sizeof(double) };
+};
+
+template <class Model, class = void>
+struct JacobianInRegisters : std::false_type
+{};
+template <class Model>
+struct JacobianInRegisters<Model, std::void_t<decltype(Model::jacobian_in_registers)>>
+  : std::bool_constant<Model::jacobian_in_registers>
+{};
+
+template <class Model, bool kStore, bool kLinearLoss>
+__global__ void __launch_bounds__(kThreads, 2)
+  k_jacobian_reg(const SweepArgs a,
+                 const int loss_type,
+                 const int* __restrict__ slot_base,
+                 double* __restrict__ partials,
+                 double* __restrict__ J_out,
+                 double* __restrict__ r_out,
+                 const long long n_points)
+{
+    if (sweep_is_gated_off(a)) {
+        return;
+    }
+    using Shape = JacobianRegShape<Model>;
+    using Pre = prepared_t<Model, GradCtx>;
+    constexpr int NP { Shape::NP };
+    constexpr int NA { Shape::NA };
+    constexpr int NT { Shape::NT };
+    constexpr int kWarps { Shape::kWarps };
+    constexpr int U { Shape::kGroup };
+    extern __shared__ double s_dyn[];
+    double* const s_pre { s_dyn }; // [2][U][3][kTile]: x, y, 1/sigma of two groups of tiles
+    __shared__ double s_par[NP];
+    __shared__ double s_red[kWarps][NT];
+    __shared__ Pre s_prep;
+    const int tid { static_cast<int>(threadIdx.x) };
+    const int lane { tid & 31 };
+    const int warp { tid >> 5 };
+    const bool tabled { a.cta_tile_begin != nullptr };
+    const int t0 { tabled ? a.cta_tile_begin[blockIdx.x]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles) * blockIdx.x
+                                             / gridDim.x) };
+    const int t1 { tabled ? a.cta_tile_begin[blockIdx.x + 1]
+                          : static_cast<int>(static_cast<long long>(a.n_tiles)
+                                             * (blockIdx.x + 1) / gridDim.x) };
+    if (t0 >= t1) {
+        return;
+    }
+    int slot { slot_base[blockIdx.x] };
+    double acc[NT];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+        acc[e] = 0.0;
+    }
+    // lanes by a shuffle tree, warps in fixed order, one partial (packed triangle)
+    const auto flush { [&]() {
+#pragma unroll
+        for (int e = 0; e < NT; ++e) {
+            const double total { warp_sum(acc[e]) };
+            acc[e] = 0.0;
+            if (lane == 0) {
+                s_red[warp][e] = total;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < NT; e += kThreads) {
+            double total { 0.0 };
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                total += s_red[w][e];
+            }
+            partials[static_cast<long long>(slot) * NT + e] = total;
+        }
+        __syncthreads();
+        ++slot;
+    } };
+    // A group = up to U consecutive tiles of one data set (contiguous in
+    // memory, only the last may be partial): one batch of asynchronous copies,
+    // one pass of the walker / loop bookkeeping for U points per thread
+    const auto group_width { [&](const TileWalker& w, const int tile) -> int {
+        return min(U, min(t1, w.tile_end) - tile);
+    } };
+    unsigned long long seen { 0ULL };
+    const auto prefetch { [&](const TileWalker& w, const int tile, const int width, const int buf) {
+        const int last_len { w.len(tile + width - 1) };
+        const long long first { w.off(tile) + tid };
+        wait_arrived(a, w.off(tile + width - 1) + last_len, seen);
+        double* dst { s_pre + buf * (U * 3 * kTile) + tid };
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u < width && (u + 1 < width || tid < last_len)) {
+                const long long i { first + u * kTile };
+                cp_async_8(dst + (3 * u) * kTile, a.x + i);
+                cp_async_8(dst + (3 * u + 1) * kTile, a.y + i);
+                cp_async_8(dst + (3 * u + 2) * kTile, a.inv_sig + i);
+            }
+        }
+        cp_async_commit();
+    } };
+    TileWalker walk {};
+    if (tabled) {
+        walk.load(a, a.cta_first_set[blockIdx.x]);
+    } else {
+        walk.seek(a, t0);
+    }
+    walk.advance_to(a, t0);
+    int width { group_width(walk, t0) };
+    int buf { 0 };
+    prefetch(walk, t0, width, 0);
+    int t { t0 };
+    int cur_set { -1 };
+    while (t < t1) {
+        walk.advance_to(a, t);
+        if (walk.set != cur_set) {
+            if (cur_set >= 0) {
+                flush();
+            }
+            __syncthreads(); // everyone is done with the previous parameters
+            if (tid < NP) {
+                s_par[tid] = a.par[static_cast<long long>(walk.set) * NP + tid];
+            }
+            __syncthreads();
+            if constexpr (HasPrepare<Model, GradCtx>) {
+                if (tid < 32) { // one warp, a table entry per lane
+                    GradCtx pc { s_par, a.status };
+                    pc.prep_lane = tid;
+                    pc.prep_lanes = 32;
+                    store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
+                }
+                __syncthreads();
+            }
+            cur_set = walk.set;
+        }
+        // the next group goes on its way, this one has landed
+        const int t_next { t + width };
+        int width_next { 0 };
+        if (t_next < t1) {
+            TileWalker next { walk };
+            next.advance_to(a, t_next);
+            width_next = group_width(next, t_next);
+            prefetch(next, t_next, width_next, buf ^ 1);
+            cp_async_wait_all_but_one();
+        } else {
+            cp_async_wait_all();
+        }
+        const int last_len { walk.len(t + width - 1) };
+        const double* src { s_pre + buf * (U * 3 * kTile) + tid };
+        const long long first { walk.off(t) + tid };
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u < width && (u + 1 < width || tid < last_len)) {
+                const double px { src[(3 * u) * kTile] };
+                const double py { src[(3 * u + 1) * kTile] };
+                double inv_sig { src[(3 * u + 2) * kTile] };
+                const long long i { first + u * kTile };
+                if (a.first_touch != 0) { // pipelined upload: sigma -> 1 / sigma, in place
+                    inv_sig = 1.0 / inv_sig;
+                    const_cast<double*>(a.inv_sig)[i] = inv_sig;
+                }
+                const auto f {
+                    evaluate_prepared(Model {}, GradCtx { s_par, a.status }, s_prep, px)
+                };
+                // lm_solver.cpp:303-310,315-317 with 1/sigma hoisted out of the row
+                const double res { (py - f.val) * inv_sig };
+                const double wgt { kLinearLoss ? 1.0 : loss_weight(loss_type, res) };
+                const double scale { kLinearLoss ? inv_sig : wgt * inv_sig };
+                double g[NP];
+                dense_gradient<NP>(f, g);
+                double row[NA];
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    row[k] = g[k] * scale;
+                }
+                row[NP] = wgt * res;
+                if constexpr (kStore) {
+                    if (J_out != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) {
+                            J_out[static_cast<long long>(k) * n_points + i] = row[k];
+                        }
+                    }
+                    if (r_out != nullptr) {
+                        r_out[i] = row[NP];
+                    }
+                }
+                // M_s += a a' (upper triangle, packed row major)
+                static_for<0, NA>([&](auto I) {
+                    static_for<I, NA>([&](auto J) {
+                        constexpr int e { tri_index(NA, I, J) };
+                        acc[e] = ::fma(row[I], row[J], acc[e]);
+                    });
+                });
+            }
+        }
+        t = t_next;
+        width = width_next;
+        buf ^= 1;
+    }
+    flush();
+}
+
 // ------------------------------------------- Jacobian, warp-specialised
 //
 // k_jacobian above makes every warp alternate between evaluating its 32

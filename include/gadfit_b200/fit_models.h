@@ -86,7 +86,8 @@ struct GaussLinearBg
     static constexpr int n_pars { 6 };
     static constexpr const char* name { "gauss_linear_bg" };
     static constexpr int chi2_unroll { 8 };
-    static constexpr int jacobian_blocks { 4 }; // tuning hint, see csrc/sweep_kernels.cuh
+    static constexpr int jacobian_blocks { 4 }; // tuning hints, see csrc/sweep_kernels.cuh
+    static constexpr bool jacobian_in_registers { true };
     template <class Ctx>
     GADFIT_HD auto prepare(const Ctx& c) const
     {
