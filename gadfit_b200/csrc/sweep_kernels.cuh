@@ -125,7 +125,15 @@ template <class Model>
 struct Chi2Tuning<Model, std::void_t<decltype(Model::chi2_unroll)>>
 {
     static constexpr int unroll { Model::chi2_unroll };
-    static constexpr int min_blocks { Model::chi2_unroll >= 8 ? 2 : 4 };
+    // resident CTAs per SM the sweep is compiled for: `chi2_blocks` if the
+    // function states it, else 2 (128 registers) from 8 points per thread
+    static constexpr int min_blocks { [] {
+        if constexpr (requires { Model::chi2_blocks; }) {
+            return Model::chi2_blocks;
+        } else {
+            return Model::chi2_unroll >= 8 ? 2 : 4;
+        }
+    }() };
 };
 // Unrolled sweeps can stage x, y, 1/sigma of the NEXT group of tiles in shared
 // memory (LDGSTS, two buffers of `unroll` tiles) while the current group is

@@ -110,6 +110,11 @@ struct ConvExpGauss
 {
     static constexpr int n_pars { 5 };
     static constexpr const char* name { "conv_exp_gauss" };
+    // chi2 sweep: 4 points per thread with 128 registers (measured, r02r: 528 ->
+    // 471 us per sweep on config 4; the 225-node function of config 5 is fastest
+    // with one point and 64 registers)
+    static constexpr int chi2_unroll { 4 };
+    static constexpr int chi2_blocks { 2 };
     static constexpr double upper_bound { 10.0 };
     static constexpr double sqrt_pi { 1.7724538509055160272981674833411451 };
 
