@@ -255,7 +255,14 @@ struct ModelOpsImpl final : ModelOps
               const TrialFinish& fin) const -> void override
     {
         if constexpr (Chi2Shape<Model>::staged) {
-            if (chi2_staged_fits && a.n_tiles >= static_cast<long long>(kChi2StagedMinTiles) * grid) {
+            // GADFIT_B200_CHI2=staged|direct overrides the choice (A/B runs, tests)
+            const char* force { std::getenv("GADFIT_B200_CHI2") };
+            const bool by_size { a.n_tiles >= static_cast<long long>(kChi2StagedMinTiles) * grid };
+            const bool staged { force != nullptr && std::strcmp(force, "staged") == 0
+                                  ? true
+                                  : (force != nullptr && std::strcmp(force, "direct") == 0 ? false
+                                                                                           : by_size) };
+            if (chi2_staged_fits && staged) {
                 k_chi2<Model, true><<<grid, kThreads, Chi2Shape<Model>::smem_bytes, st>>>(
                   a, partials, fin);
                 return;

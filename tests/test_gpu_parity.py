@@ -424,3 +424,71 @@ def test_distinct_solvers_on_concurrent_host_threads(c1):
     assert not errors, errors
     for sc, res in zip(todo, results):
         _check_kat(sc, res, c1, tol_floor=1e-11)
+
+
+# ---- round 2: kernel variants chosen by shape must agree with each other -----
+
+@pytest.mark.parametrize("name,kwargs,variants", [
+    ("C3", dict(n_sets=40, n_points=3000, iteration_limit=3), ("reg", "sp", "ws")),
+    ("C2", dict(n_sets=3, n_points=40_000, iteration_limit=3), ("ws", "sp")),
+    ("C4", dict(n_sets=6, n_points=2000, iteration_limit=3), ("sp", "ws")),
+])
+def test_jacobian_sweep_variants_agree(name, kwargs, variants, monkeypatch):
+    """The three Jacobian sweeps (warp-specialised DMMA, software-pipelined
+    DMMA, accumulated in registers; csrc/sweep_kernels.cuh) differ only in the
+    order of the sums: J^T J, J^T r to 1e-12 of the diagonal scale, identical
+    decisions, parameters to 1e-10."""
+    from gadfit_b200 import LMsolver, workloads as W
+    results = []
+    for v in variants:
+        monkeypatch.setenv("GADFIT_B200_JAC", v)
+        w = W.WORKLOADS[name](**kwargs)
+        s = LMsolver(w.model)
+        w.setup(s)
+        s.fit(w.lambda0)
+        n = int(round(np.sqrt(s.getJTJ().size)))
+        results.append(dict(jtj=s.getJTJ().reshape(n, n), rhs=s.getRightSide(),
+                            decisions=[t["decision"] for t in s.trace()], chi2=s.chi2(),
+                            pars=np.array([[s.getParValue(k, j) for k in range(w.n_pars)]
+                                           for j in range(w.n_sets)])))
+    ref = results[0]
+    scale = np.sqrt(np.abs(np.diag(ref["jtj"])))
+    for r in results[1:]:
+        assert r["decisions"] == ref["decisions"]
+        np.testing.assert_allclose(r["jtj"] / scale[:, None] / scale[None, :],
+                                   ref["jtj"] / scale[:, None] / scale[None, :], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r["rhs"] / scale, ref["rhs"] / scale, rtol=0,
+                                   atol=1e-11 * np.max(np.abs(ref["rhs"] / scale)))
+        np.testing.assert_allclose(r["chi2"], ref["chi2"], rtol=1e-12)
+        np.testing.assert_allclose(r["pars"], ref["pars"], rtol=1e-10, atol=1e-13)
+
+
+def test_staged_chi2_sweep_is_bit_identical_to_the_direct_one(monkeypatch):
+    """The chi2 sweep with inputs staged through shared memory (long tile
+    ranges) adds the same terms in the same order as the one with direct loads:
+    the whole trace must be identical to the last bit."""
+    from gadfit_b200 import LMsolver, workloads as W
+    traces = []
+    for v in ("direct", "staged"):
+        monkeypatch.setenv("GADFIT_B200_CHI2", v)
+        w = W.WORKLOADS["C2"](n_sets=3, n_points=70_001, iteration_limit=3)  # ragged last tile
+        s = LMsolver(w.model)
+        w.setup(s)
+        s.fit(w.lambda0)
+        traces.append(([(t["decision"], t["new_chi2"], t["lambda_"]) for t in s.trace()], s.chi2()))
+    assert traces[0] == traces[1]
+
+
+def test_phase_timers_can_be_switched_off(c1):
+    """gadfit_b200_set_phase_timers(0): no event records on the stream, the fit
+    itself is unchanged; the whole-fit timer keeps running."""
+    sc = scenarios.C1_SCENARIOS[0]
+    a, lam, _, _ = scenarios.build(sc, backends.product_solver(), c1)
+    a.fit(lam)
+    b, _, _, _ = scenarios.build(sc, backends.product_solver(), c1)
+    b.setPhaseTimers(False)
+    b.fit(lam)
+    assert [t["new_chi2"] for t in a.trace()] == [t["new_chi2"] for t in b.trace()]
+    ta, tb = a.timings(), b.timings()
+    assert ta["jacobian"][0] > 0.0 and tb["jacobian"][0] == 0.0
+    assert tb["main"][0] > 0.0 and tb["jacobian"][1] == ta["jacobian"][1]
