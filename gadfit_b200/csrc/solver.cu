@@ -314,6 +314,10 @@ struct SolverImpl
     int NP { 0 };
     std::vector<DataSet> sets;
     std::vector<double> par;         // [S][NP]
+    // page-locked view of `par` for the gather of all ranks' parameters at the
+    // end of a multi-GPU fit (pageable: ~7 GB/s, 45 MB for config 5 on 8 GPUs)
+    void* par_registered { nullptr };
+    size_t par_registered_bytes { 0 };
     std::vector<int> n_set_pars;     // FitFunction::getNumPars per data set
     std::vector<unsigned> active;    // Indices::active as bit masks
     unsigned global_mask { 0U };     // Indices::global
@@ -415,6 +419,9 @@ struct SolverImpl
         if (comm != nullptr) {
             Nccl::instance().commDestroy(comm);
         }
+        if (par_registered != nullptr) {
+            cudaHostUnregister(par_registered);
+        }
         if (h_mirror != nullptr) {
             cudaFreeHost(h_mirror);
         }
@@ -451,6 +458,10 @@ struct SolverImpl
             throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "negative number of points" };
         }
         sets.push_back({ n, x, y, e });
+        if (par_registered != nullptr) { // the vector may move
+            cudaHostUnregister(par_registered);
+            par_registered = nullptr;
+        }
         par.resize(sets.size() * NP, 0.0);
         n_set_pars.push_back(0);
         // A new data set starts as a copy of the fitting function of the
@@ -919,6 +930,20 @@ struct SolverImpl
                                                 stream));
             }
             all_reduce(d_stage.ptr, all);
+            const size_t bytes { all * sizeof(double) };
+            if (bytes >= (size_t { 1 } << 20)
+                && (par_registered != par.data() || par_registered_bytes != bytes)) {
+                if (par_registered != nullptr) {
+                    cudaHostUnregister(par_registered);
+                    par_registered = nullptr;
+                }
+                if (cudaHostRegister(par.data(), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+                    par_registered = par.data();
+                    par_registered_bytes = bytes;
+                } else {
+                    cudaGetLastError(); // not fatal: the copy is then a pageable one
+                }
+            }
             GADFIT_CUDA_TRY(cudaMemcpyAsync(par.data(),
                                             d_stage.ptr,
                                             all * sizeof(double),
