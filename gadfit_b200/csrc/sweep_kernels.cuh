@@ -1522,8 +1522,20 @@ __global__ void __launch_bounds__(kJacThreads, 2)
 // weight), immediately contracted with the stored weighted Jacobian rows:
 // v_s[k] = sum_i J_ik omega_i (the dgemv of lm_solver.cpp:383), one partial
 // vector of NP entries per (CTA, data-set run).
+// Resident CTAs per SM the sweep is compiled for: `omega_blocks` if the
+// function states it (config 4's single-integral function: 3, i.e. 80
+// registers instead of 100 -- 1028 -> 990 us per sweep, r02u), else no cap
 template <class Model>
-__global__ void __launch_bounds__(kThreads)
+constexpr int omega_min_blocks()
+{
+    if constexpr (requires { Model::omega_blocks; }) {
+        return Model::omega_blocks;
+    } else {
+        return 1;
+    }
+}
+template <class Model>
+__global__ void __launch_bounds__(kThreads, omega_min_blocks<Model>())
   k_omega(const SweepArgs a,
           const double* __restrict__ seed, // [n_sets][NP] delta1 by parameter
           const double* __restrict__ J,    // [NP][n_points]

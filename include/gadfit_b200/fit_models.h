@@ -115,6 +115,11 @@ struct ConvExpGauss
     // with one point and 64 registers)
     static constexpr int chi2_unroll { 4 };
     static constexpr int chi2_blocks { 2 };
+    // Jacobian sweep with 4 CTAs per SM (64 registers: 891 -> 848 us per sweep),
+    // omega sweep with 3 (80 registers: 1028 -> 990 us), measured r02u; the
+    // 225-node function of config 5 is fastest with the default 2 (128 registers)
+    static constexpr int jacobian_blocks { 4 };
+    static constexpr int omega_blocks { 3 };
     static constexpr double upper_bound { 10.0 };
     static constexpr double sqrt_pi { 1.7724538509055160272981674833411451 };
 
