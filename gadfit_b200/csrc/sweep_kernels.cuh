@@ -466,10 +466,8 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
         __syncthreads();
         if constexpr (HasPrepare<Model, ValueCtx>) {
             if (tid < 32) { // one warp, a table entry per lane (fit_function.h: tabulate)
-                ValueCtx pc { s_par, a.status };
-                pc.prep_lane = tid;
-                pc.prep_lanes = 32;
-                store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
+                const Cooperative<ValueCtx> pc { ValueCtx { s_par, a.status }, tid };
+                store_prepared(prepare_of(Model {}, pc), s_prep, tid);
             }
             __syncthreads();
         }
@@ -942,10 +940,8 @@ __global__ void __launch_bounds__(kThreads, JacobianTuning<Model>::min_blocks)
         __syncthreads();
         if constexpr (HasPrepare<Model, GradCtx>) {
             if (tid < 32) { // one warp, a table entry per lane
-                GradCtx pc { s_par, a.status };
-                pc.prep_lane = tid;
-                pc.prep_lanes = 32;
-                store_prepared(prepare_of(Model {}, pc), *s_prep, tid, 32);
+                const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
+                store_prepared(prepare_of(Model {}, pc), *s_prep, tid);
             }
             __syncthreads();
         }
@@ -1134,10 +1130,8 @@ __global__ void __launch_bounds__(kThreads, 2)
             __syncthreads();
             if constexpr (HasPrepare<Model, GradCtx>) {
                 if (tid < 32) { // one warp, a table entry per lane
-                    GradCtx pc { s_par, a.status };
-                    pc.prep_lane = tid;
-                    pc.prep_lanes = 32;
-                    store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
+                    const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
+                    store_prepared(prepare_of(Model {}, pc), s_prep, tid);
                 }
                 __syncthreads();
             }
@@ -1359,10 +1353,8 @@ __global__ void __launch_bounds__(kJacThreads, 2)
                 named_bar_sync(kBarEval, kTile);
                 if constexpr (HasPrepare<Model, GradCtx>) {
                     if (tid < 32) { // one warp, a table entry per lane
-                        GradCtx pc { s_par, a.status };
-                        pc.prep_lane = tid;
-                        pc.prep_lanes = 32;
-                        store_prepared(prepare_of(Model {}, pc), *s_prep, tid, 32);
+                        const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
+                        store_prepared(prepare_of(Model {}, pc), *s_prep, tid);
                     }
                     named_bar_sync(kBarEval, kTile);
                 }
@@ -1598,10 +1590,8 @@ __global__ void __launch_bounds__(kThreads, omega_min_blocks<Model>())
             __syncthreads();
             if constexpr (HasPrepare<Model, Dir2Ctx>) {
                 if (tid < 32) {
-                    Dir2Ctx pc { s_par, s_seed, a.status };
-                    pc.prep_lane = tid;
-                    pc.prep_lanes = 32;
-                    store_prepared(prepare_of(Model {}, pc), s_prep, tid, 32);
+                    const Cooperative<Dir2Ctx> pc { Dir2Ctx { s_par, s_seed, a.status }, tid };
+                    store_prepared(prepare_of(Model {}, pc), s_prep, tid);
                 }
                 __syncthreads();
             }

@@ -94,10 +94,6 @@ struct ValueCtx : QuadratureMixin
 {
     const double* p;
     unsigned* status; // sweep-wide status word (device memory) or nullptr
-    // cooperative prepare(): this thread fills the table entries
-    // i = prep_lane, prep_lane + prep_lanes, ... (tabulate() below)
-    int prep_lane { 0 };
-    int prep_lanes { 1 };
     GADFIT_HD explicit ValueCtx(const double* p, unsigned* status = nullptr)
       : p { p }, status { status }
     {}
@@ -133,8 +129,6 @@ struct GradCtx : QuadratureMixin
 {
     const double* p;
     unsigned* status;
-    int prep_lane { 0 };
-    int prep_lanes { 1 };
     GADFIT_HD explicit GradCtx(const double* p, unsigned* status = nullptr)
       : p { p }, status { status }
     {}
@@ -175,8 +169,6 @@ struct Dir2Ctx : QuadratureMixin
     // Direction: delta1 of the column this parameter maps to, 0 if passive
     const double* seed;
     unsigned* status;
-    int prep_lane { 0 };
-    int prep_lanes { 1 };
     GADFIT_HD Dir2Ctx(const double* p, const double* seed, unsigned* status = nullptr)
       : p { p }, seed { seed }, status { status }
     {}
@@ -218,50 +210,96 @@ GADFIT_HD auto par(const Ctx& c)
 // ---- prepare hook ----------------------------------------------------------
 //
 // Tables inside what prepare() returns: tabulate<N>(c, f) = { f(0), ..., f(N-1) }.
-// On the device the sweeps run prepare() on the 32 lanes of one warp at once:
-// each lane evaluates only the entries i = lane (mod 32) of every table (so a
-// table of exp() at 15 quadrature nodes costs one exp() of latency, not 15)
-// and store_prepared() below merges the lanes' parts in shared memory.
-// Contexts without prep_lane / prep_lanes members (the reference's AdVar, the
-// oracle's dual) fill the whole table.
+// On the device the sweeps run prepare() on the 32 lanes of one warp at once,
+// with the context wrapped in Cooperative<Ctx>: tabulate() then evaluates and
+// returns only the entries i = lane (mod 32) of every table -- a LaneTable of
+// ceil(N / 32) entries that lives in registers, so a table of exp() at 15
+// quadrature nodes costs one exp() of latency, not 15, and a 15 x 15 table
+// seven -- and store_prepared() below scatters the lanes' parts into the full
+// Table in shared memory.  Plain contexts (the reference's AdVar, the oracle's
+// dual, a device context outside a sweep) fill the whole table.
+constexpr int k_prepare_lanes { 32 };
+
+template <class Ctx>
+struct Cooperative : Ctx
+{
+    int lane;
+    GADFIT_HD Cooperative(const Ctx& c, const int lane) : Ctx { c }, lane { lane } {}
+};
+template <class T>
+struct is_cooperative : std::false_type
+{};
+template <class Ctx>
+struct is_cooperative<Cooperative<Ctx>> : std::true_type
+{};
+
 template <class T, int N>
 struct Table
 {
     T v[N];
     GADFIT_HD const T& operator[](const int i) const { return v[i]; }
 };
+// One lane's entries of a Table<T, N>: v[k] = entry lane + 32 k
+template <class T, int N>
+struct LaneTable
+{
+    static constexpr int per_lane { (N + k_prepare_lanes - 1) / k_prepare_lanes };
+    T v[per_lane];
+};
 
 template <int N, class Ctx, class F>
 GADFIT_HD auto tabulate(const Ctx& c, F&& f)
 {
     using T = decltype(f(0));
-    Table<T, N> t;
-    if constexpr (requires { c.prep_lane; }) {
-        for (int i = c.prep_lane; i < N; i += c.prep_lanes) {
-            t.v[i] = f(i);
+    if constexpr (is_cooperative<Ctx>::value) {
+        LaneTable<T, N> t;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < LaneTable<T, N>::per_lane; ++k) {
+            const int i { c.lane + k_prepare_lanes * k };
+            t.v[k] = f(i < N ? i : N - 1); // (past the end: a valid entry, not stored)
         }
+        return t;
     } else {
+        Table<T, N> t;
         for (int i = 0; i < N; ++i) {
             t.v[i] = f(i);
         }
+        return t;
     }
-    return t;
 }
 
 // dst <- the part of `mine` this lane is responsible for: its entries of every
 // Table, everything else from lane 0 (every lane computed the same value)
+template <class... Ts>
+struct Pack;
 template <class T>
-GADFIT_HD void store_prepared(const T& mine, T& dst, const int lane, const int)
+struct is_pack : std::false_type
+{};
+template <class... Ts>
+struct is_pack<Pack<Ts...>> : std::true_type
+{};
+
+template <class T>
+    requires(!is_pack<T>::value)
+GADFIT_HD void store_prepared(const T& mine, T& dst, const int lane)
 {
     if (lane == 0) {
         dst = mine;
     }
 }
 template <class T, int N>
-GADFIT_HD void store_prepared(const Table<T, N>& mine, Table<T, N>& dst, const int lane, const int lanes)
+GADFIT_HD void store_prepared(const LaneTable<T, N>& mine, Table<T, N>& dst, const int lane)
 {
-    for (int i = lane; i < N; i += lanes) {
-        dst.v[i] = mine.v[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < LaneTable<T, N>::per_lane; ++k) {
+        const int i { lane + k_prepare_lanes * k };
+        if (i < N) {
+            dst.v[i] = mine.v[k];
+        }
     }
 }
 // A heterogeneous aggregate for what prepare() returns: pack(a, b, c) keeps
@@ -296,12 +334,14 @@ GADFIT_HD Pack<T, Ts...> pack(const T& v, const Ts&... rest)
     return { v, pack(rest...) };
 }
 
-template <class T, class... Ts>
-GADFIT_HD void store_prepared(const Pack<T, Ts...>& mine, Pack<T, Ts...>& dst, const int lane, const int lanes)
+// (element by element: a LaneTable of `mine` goes into the Table of `dst`)
+template <class A, class... As, class B, class... Bs>
+GADFIT_HD void store_prepared(const Pack<A, As...>& mine, Pack<B, Bs...>& dst, const int lane)
 {
-    store_prepared(mine.head, dst.head, lane, lanes);
-    if constexpr (sizeof...(Ts) > 0) {
-        store_prepared(mine.tail, dst.tail, lane, lanes);
+    static_assert(sizeof...(As) == sizeof...(Bs));
+    store_prepared(mine.head, dst.head, lane);
+    if constexpr (sizeof...(As) > 0) {
+        store_prepared(mine.tail, dst.tail, lane);
     }
 }
 

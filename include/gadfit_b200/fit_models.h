@@ -158,11 +158,13 @@ struct LorentzDoubleInt
     static constexpr int n_pars { 7 };
     static constexpr const char* name { "lorentz_double_int" };
 
-    // The exponential factorises, e^{-k1 u^2 - k2 v^2} = e^{-k1 u^2} e^{-k2 v^2},
-    // and each factor depends on the parameters and ONE node index only: 30
-    // exponentials per data set instead of 225 per data point.
-    // get<0>: e^{-k1 u_i^2} (inner node i), get<1>: e^{-k2 v_j^2} (outer node
-    // j), get<2>: gamma^2
+    // e^{-k1 u_i^2 - k2 v_j^2} depends on the parameters and the node pair
+    // (i, j) only: a table of 15 x 15 exponentials per DATA SET (one warp fills
+    // it, seven entries per lane) instead of 225 exponentials -- or, with the
+    // factorised form used until round 2, 225 products of two table entries
+    // and their tangents -- per data POINT.
+    // get<0>: e^{-k1 u_i^2 - k2 v_j^2} at [15 i + j] (inner node i, outer node
+    // j), get<1>: gamma^2
     template <class Ctx>
     GADFIT_HD auto prepare(const Ctx& c) const
     {
@@ -173,20 +175,24 @@ struct LorentzDoubleInt
             const double node { kronrod_node(i, 0.0, 1.0) };
             return node * node;
         } };
-        return pack(tabulate<k15_size>(c, [&](const int i) { return exp(-(k1 * node_sq(i))); }),
-                    tabulate<k15_size>(c, [&](const int i) { return exp(-(k2 * node_sq(i))); }),
+        return pack(tabulate<k15_size * k15_size>(c,
+                                                  [&](const int ij) {
+                                                      const int i { ij / k15_size };
+                                                      const int j { ij - i * k15_size };
+                                                      return exp(-(k1 * node_sq(i) + k2 * node_sq(j)));
+                                                  }),
                     g * g);
     }
     template <class Ctx, class Pre>
     GADFIT_HD auto operator()(const Ctx& c, const Pre& pre, const double x) const
     {
         const auto dx { x - par<1>(c) };
-        const auto& g2 { pre.template get<2>() };
+        const auto& g2 { pre.template get<1>() };
         const auto lorentz { par<0>(c) * g2 / (dx * dx + g2) };
         const auto integral { c.kronrod2d_indexed(
           0.0, 1.0, 0.0, 1.0, [&](const auto& u, const auto& v, const int i, const int j) {
               const auto s { x - u - v };
-              return pre.template get<0>()[i] * pre.template get<1>()[j] / (1.0 + s * s);
+              return pre.template get<0>()[i * k15_size + j] / (1.0 + s * s);
           }) };
         return lorentz + par<3>(c) + par<4>(c) * integral;
     }
