@@ -465,10 +465,9 @@ __global__ void __launch_bounds__(kThreads, Chi2Tuning<Model>::min_blocks)
         }
         __syncthreads();
         if constexpr (HasPrepare<Model, ValueCtx>) {
-            if (tid < 32) { // one warp, a table entry per lane (fit_function.h: tabulate)
-                const Cooperative<ValueCtx> pc { ValueCtx { s_par, a.status }, tid };
-                store_prepared(prepare_of(Model {}, pc), s_prep, tid);
-            }
+            // every evaluation thread fills the table entries tid, tid + 256, ...
+            const Cooperative<ValueCtx> pc { ValueCtx { s_par, a.status }, tid };
+            store_prepared(prepare_of(Model {}, pc), s_prep, tid);
             __syncthreads();
         }
         cur_set = walk.set;
@@ -939,10 +938,9 @@ __global__ void __launch_bounds__(kThreads, JacobianTuning<Model>::min_blocks)
         }
         __syncthreads();
         if constexpr (HasPrepare<Model, GradCtx>) {
-            if (tid < 32) { // one warp, a table entry per lane
-                const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
-                store_prepared(prepare_of(Model {}, pc), *s_prep, tid);
-            }
+            // every evaluation thread fills the table entries tid, tid + 256, ...
+            const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
+            store_prepared(prepare_of(Model {}, pc), *s_prep, tid);
             __syncthreads();
         }
         const int run_begin { t };
@@ -1129,10 +1127,9 @@ __global__ void __launch_bounds__(kThreads, 2)
             }
             __syncthreads();
             if constexpr (HasPrepare<Model, GradCtx>) {
-                if (tid < 32) { // one warp, a table entry per lane
-                    const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
-                    store_prepared(prepare_of(Model {}, pc), s_prep, tid);
-                }
+                // every evaluation thread fills the table entries tid, tid + 256, ...
+                const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
+                store_prepared(prepare_of(Model {}, pc), s_prep, tid);
                 __syncthreads();
             }
             cur_set = walk.set;
@@ -1352,10 +1349,9 @@ __global__ void __launch_bounds__(kJacThreads, 2)
                 }
                 named_bar_sync(kBarEval, kTile);
                 if constexpr (HasPrepare<Model, GradCtx>) {
-                    if (tid < 32) { // one warp, a table entry per lane
-                        const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
-                        store_prepared(prepare_of(Model {}, pc), *s_prep, tid);
-                    }
+                    // every evaluation thread fills the table entries tid, tid + 256, ...
+                    const Cooperative<GradCtx> pc { GradCtx { s_par, a.status }, tid };
+                    store_prepared(prepare_of(Model {}, pc), *s_prep, tid);
                     named_bar_sync(kBarEval, kTile);
                 }
                 cur_set = walk.set;
@@ -1589,10 +1585,9 @@ __global__ void __launch_bounds__(kThreads, omega_min_blocks<Model>())
             }
             __syncthreads();
             if constexpr (HasPrepare<Model, Dir2Ctx>) {
-                if (tid < 32) {
-                    const Cooperative<Dir2Ctx> pc { Dir2Ctx { s_par, s_seed, a.status }, tid };
-                    store_prepared(prepare_of(Model {}, pc), s_prep, tid);
-                }
+                // every evaluation thread fills the table entries tid, tid + 256, ...
+                const Cooperative<Dir2Ctx> pc { Dir2Ctx { s_par, s_seed, a.status }, tid };
+                store_prepared(prepare_of(Model {}, pc), s_prep, tid);
                 __syncthreads();
             }
             cur_set = walk.set;

@@ -210,15 +210,15 @@ GADFIT_HD auto par(const Ctx& c)
 // ---- prepare hook ----------------------------------------------------------
 //
 // Tables inside what prepare() returns: tabulate<N>(c, f) = { f(0), ..., f(N-1) }.
-// On the device the sweeps run prepare() on the 32 lanes of one warp at once,
-// with the context wrapped in Cooperative<Ctx>: tabulate() then evaluates and
-// returns only the entries i = lane (mod 32) of every table -- a LaneTable of
-// ceil(N / 32) entries that lives in registers, so a table of exp() at 15
-// quadrature nodes costs one exp() of latency, not 15, and a 15 x 15 table
-// seven -- and store_prepared() below scatters the lanes' parts into the full
-// Table in shared memory.  Plain contexts (the reference's AdVar, the oracle's
+// On the device the 256 evaluation threads of a sweep's CTA run prepare()
+// together, with the context wrapped in Cooperative<Ctx>: tabulate() then
+// evaluates and returns only the entries i = lane (mod 256) of every table -- a
+// LaneTable of ceil(N / 256) entries that lives in registers, so a table of
+// exp() at 15 quadrature nodes, or at 15 x 15 node pairs, costs one exp() of
+// latency -- and store_prepared() below scatters the lanes' parts into the
+// full Table in shared memory.  Plain contexts (the reference's AdVar, the oracle's
 // dual, a device context outside a sweep) fill the whole table.
-constexpr int k_prepare_lanes { 32 };
+constexpr int k_prepare_lanes { 256 };
 
 template <class Ctx>
 struct Cooperative : Ctx
@@ -239,7 +239,7 @@ struct Table
     T v[N];
     GADFIT_HD const T& operator[](const int i) const { return v[i]; }
 };
-// One lane's entries of a Table<T, N>: v[k] = entry lane + 32 k
+// One lane's entries of a Table<T, N>: v[k] = entry lane + 256 k
 template <class T, int N>
 struct LaneTable
 {
