@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <charconv>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -299,6 +300,28 @@ struct SlotTable
 } // namespace
 
 // State and phases of one solver; the opaque C handle derives from it
+// GADFIT_B200_TRACE_HOST=1: wall-clock time of the host-side phases of fit()
+// to stderr (developer aid for the multi-GPU set-up / gather costs)
+struct HostPhase
+{
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit HostPhase(const char* name)
+      : name { name }, t0 { std::chrono::steady_clock::now() },
+        on { std::getenv("GADFIT_B200_TRACE_HOST") != nullptr }
+    {}
+    ~HostPhase()
+    {
+        if (on) {
+            const double ms { std::chrono::duration<double, std::milli>(
+                                std::chrono::steady_clock::now() - t0)
+                                .count() };
+            std::fprintf(stderr, "[gadfit_b200 host] %-28s %9.3f ms\n", name, ms);
+        }
+    }
+};
+
 struct SolverImpl
 {
     // ---- problem description (host; mirrors the private state of LMsolver,
@@ -314,6 +337,7 @@ struct SolverImpl
     int NP { 0 };
     std::vector<DataSet> sets;
     std::vector<double> par;         // [S][NP]
+    bool indexing_dirty { true };    // data sets or parameter roles changed since prepare_indexing()
     // page-locked view of `par` for the gather of all ranks' parameters at the
     // end of a multi-GPU fit (pageable: ~7 GB/s, 45 MB for config 5 on 8 GPUs)
     void* par_registered { nullptr };
@@ -458,6 +482,7 @@ struct SolverImpl
             throw StatusError { GADFIT_B200_INVALID_ARGUMENT, "negative number of points" };
         }
         sets.push_back({ n, x, y, e });
+        indexing_dirty = true;
         if (par_registered != nullptr) { // the vector may move
             cudaHostUnregister(par_registered);
             par_registered = nullptr;
@@ -485,6 +510,18 @@ struct SolverImpl
         }
         set_par_called = true;
         const unsigned bit { 1U << i_par };
+        // (the column map is rebuilt at the next fit() only if a role changed)
+        const unsigned old_global { global_mask };
+        const auto assign { [&](const int s) {
+            par[static_cast<size_t>(s) * NP + i_par] = val;
+            const int n_pars_new { std::max(n_set_pars[s], i_par + 1) };
+            const unsigned active_new { is_active ? (active[s] | bit) : (active[s] & ~bit) };
+            if (n_pars_new != n_set_pars[s] || active_new != active[s]) {
+                indexing_dirty = true;
+            }
+            n_set_pars[s] = n_pars_new;
+            active[s] = active_new;
+        } };
         if (i_dataset == -1) {
             // lm_solver.cpp:73-88
             if (is_active) {
@@ -493,17 +530,15 @@ struct SolverImpl
                 global_mask &= ~bit;
             }
             for (int s = 0; s < S; ++s) {
-                par[static_cast<size_t>(s) * NP + i_par] = val;
-                n_set_pars[s] = std::max(n_set_pars[s], i_par + 1);
-                active[s] = is_active ? (active[s] | bit) : (active[s] & ~bit);
+                assign(s);
             }
         } else {
             // lm_solver.cpp:89-98
             global_mask &= ~bit;
-            par[static_cast<size_t>(i_dataset) * NP + i_par] = val;
-            n_set_pars[i_dataset] = std::max(n_set_pars[i_dataset], i_par + 1);
-            active[i_dataset] =
-              is_active ? (active[i_dataset] | bit) : (active[i_dataset] & ~bit);
+            assign(i_dataset);
+        }
+        if (global_mask != old_global) {
+            indexing_dirty = true;
         }
     }
 
@@ -513,6 +548,9 @@ struct SolverImpl
         const int S { static_cast<int>(sets.size()) };
         if (S == 0) {
             throw StatusError { GADFIT_B200_NO_FITTING_PARAMETERS, "no data sets" };
+        }
+        if (!indexing_dirty) {
+            return; // same data sets and parameter roles as at the last successful call
         }
         n_active = 0;
         for (const unsigned a : active) {
@@ -564,6 +602,7 @@ struct SolverImpl
             throw StatusError { GADFIT_B200_NO_FITTING_PARAMETERS,
                                 "no active fitting parameters" };
         }
+        indexing_dirty = false;
     }
 
     // Column of parameter k of data set s, -1 if passive
@@ -915,6 +954,7 @@ struct SolverImpl
 
     auto download_parameters() -> void
     {
+        const HostPhase phase { "download_parameters" };
         const size_t n { static_cast<size_t>(n_local_sets) * NP };
         if (world > 1 && !part.split) {
             // Every rank ends up with the parameters of every data set: each
@@ -1718,7 +1758,10 @@ struct SolverImpl
             return;
         }
         stop_reason = GADFIT_B200_STOP_ITERATION_LIMIT;
-        prepare_indexing();
+        {
+            const HostPhase phase { "prepare_indexing" };
+            prepare_indexing();
+        }
         ensure_device();
         // Data not in HBM yet: the copies are enqueued chunk by chunk on a copy
         // stream and not waited for; the FIRST Jacobian sweep (launched ahead of
@@ -1726,9 +1769,15 @@ struct SolverImpl
         // their arrival, so that sweep and all the set-up below overlap the
         // PCIe transfer.
         const bool fresh_upload { !data_uploaded && settings.iteration_limit != 0 };
-        upload_parameters(fresh_upload);
+        {
+            const HostPhase phase { "upload_parameters" };
+            upload_parameters(fresh_upload);
+        }
         reset_timers();
-        init_damping();
+        {
+            const HostPhase phase { "init_damping" };
+            init_damping();
+        }
         const size_t n_par { static_cast<size_t>(std::max(n_local_sets, 1)) * NP };
         d_delta1_par.zero(n_par, stream);
         d_delta2_par.zero(n_par, stream);
