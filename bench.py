@@ -496,6 +496,13 @@ def main_b200(args, emit):
                 "chi2": out[0],
             }
             del s2
+        if e2e is not None:
+            # same start, same data, same iterations: the end-to-end fit (pipelined
+            # upload, sigma inverted in place by the first sweep) must land on the
+            # chi2 of the device-resident one
+            ref = med["chi2"]
+            e2e["chi2_rel_diff_to_device_resident_fit"] = (
+                abs(e2e["chi2"] - ref) / abs(ref) if ref == ref and ref != 0.0 else None)
         med["e2e"] = e2e
         return med
 
