@@ -124,6 +124,9 @@ struct ModelOpsImpl final : ModelOps
     // `jacobian_in_registers`): four more kernels per function otherwise
     static constexpr bool kHasRegisterJacobian { JacobianInRegisters<Model>::value };
     bool chi2_staged_fits { false };
+    // GADFIT_B200_CHI2=staged|direct (read at the first device use of a solver)
+    // overrides the choice by size: 1 staged, -1 direct, 0 by size (A/B runs, tests)
+    int chi2_force { 0 };
     bool small_smem_ready { false };
     static constexpr size_t kSmallSmemLimit { 200 * 1024 };
 
@@ -181,6 +184,12 @@ struct ModelOpsImpl final : ModelOps
         // overrides the choice (A/B runs).
         const char* jac { std::getenv("GADFIT_B200_JAC") };
         pipelined_jacobian = Shape::NB < 2;
+        const char* chi2_variant { std::getenv("GADFIT_B200_CHI2") };
+        chi2_force = chi2_variant == nullptr
+                       ? 0
+                       : (std::strcmp(chi2_variant, "staged") == 0
+                            ? 1
+                            : (std::strcmp(chi2_variant, "direct") == 0 ? -1 : 0));
         register_jacobian = JacobianInRegisters<Model>::value;
         if (jac != nullptr && std::strcmp(jac, "sp") == 0) {
             pipelined_jacobian = true;
@@ -255,13 +264,8 @@ struct ModelOpsImpl final : ModelOps
               const TrialFinish& fin) const -> void override
     {
         if constexpr (Chi2Shape<Model>::staged) {
-            // GADFIT_B200_CHI2=staged|direct overrides the choice (A/B runs, tests)
-            const char* force { std::getenv("GADFIT_B200_CHI2") };
             const bool by_size { a.n_tiles >= static_cast<long long>(kChi2StagedMinTiles) * grid };
-            const bool staged { force != nullptr && std::strcmp(force, "staged") == 0
-                                  ? true
-                                  : (force != nullptr && std::strcmp(force, "direct") == 0 ? false
-                                                                                           : by_size) };
+            const bool staged { chi2_force == 1 ? true : (chi2_force == -1 ? false : by_size) };
             if (chi2_staged_fits && staged) {
                 k_chi2<Model, true><<<grid, kThreads, Chi2Shape<Model>::smem_bytes, st>>>(
                   a, partials, fin);
