@@ -79,3 +79,16 @@ def test_parameters_are_readable_before_fit(c1):
     s.setPar(1, 2.5, True)
     s.setPar(2, 3.5, False, 0)
     assert [s.getParValue(k) for k in range(3)] == [1.5, 2.5, 3.5]
+
+
+def test_host_only_switches_work_without_a_gpu(c1):
+    """Round 2 entry points that touch no device state: the phase-timer switch
+    and invalidate_data, on a machine without a GPU; null handles are refused."""
+    s = g.LMsolver("exponential")
+    s.addDataset(c1["x_data_1"], c1["y_data_1"])
+    s.setPhaseTimers(False)
+    s.setPhaseTimers(True)
+    s.invalidateData()
+    api = _capi.product_api()
+    assert api.set_phase_timers(None, 1) != _capi.OK
+    assert api.invalidate_data(None) != _capi.OK
