@@ -30,6 +30,15 @@
 // oracle/ref_harness.cpp, the oracle's dual), calls prepare() at every
 // evaluation -- the same arithmetic, so the source of a function stays single.
 //
+// TUNING HINTS (optional static members of a fitting function; defaults are
+// fine for any function, every hint below is an A/B measurement on a BASELINE
+// shape, see csrc/sweep_kernels.cuh):
+//     static constexpr int  chi2_unroll;            // points per thread and loop iteration of the chi2 sweep (1; 8 for cheap closed forms)
+//     static constexpr int  chi2_blocks;            // resident CTAs per SM the chi2 sweep is compiled for (4; 2 from chi2_unroll 8)
+//     static constexpr int  jacobian_blocks;        // the same for the software-pipelined Jacobian sweep (2 = 128 registers)
+//     static constexpr bool jacobian_in_registers;  // few parameters, cheap function: M_s accumulated in registers, no tensor tiles
+//     static constexpr int  omega_blocks;           // resident CTAs per SM of the omega sweep (no cap)
+//
 // c.kronrod(...) / c.kronrod2d(...) give the fixed 15-point Kronrod panel of
 // the reference (numerical_integration.cpp:133-148,189-215); the *_indexed
 // variants also hand the integrand the node indices, so that it can look up
